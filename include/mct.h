@@ -1,0 +1,137 @@
+/*
+ * mct.h -- C ABI of libmct_sm100a.so: the B200 (sm_100a) replacement for the hot path of
+ * ModeCouplingTheory.jl v0.8.9 -- the wavenumber-resolved memory-kernel evaluation and the Fuchs
+ * time-doubling step that consumes it.  Plain pointers and sizes only; every entry point returns an int
+ * status (MCT_OK = 0) and never calls back into the host language.  Citations (file:line) are relative to
+ * the reference repository root.
+ *
+ * Data conventions (all Float64):
+ *   - Vectors over wavenumber are length Nk.  Matrices are Julia column-major: V[iq + ip*Nk] = V[iq,ip].
+ *   - Multi-component quantities are Nk blocks of Ns x Ns doubles, column-major inside a block, i.e. the
+ *     memory of a Julia Vector{SMatrix{Ns,Ns,Float64}}: X[ik*Ns*Ns + a + b*Ns] = X[ik][a,b].
+ *   - "dof" = Nk*Ns*Ns (Ns = 1 for the single-component kernels; K is then the `.diag` of the reference's
+ *     Diagonal).
+ *   - Trajectories are [nt][dof] row-major: the concatenation of the reference's Vector of per-time arrays.
+ *   - Unless a function name ends in _dev, every pointer is a HOST pointer owned by the caller; the library
+ *     copies in/out.  Handles own device memory and one CUDA stream; a handle must not be used from two
+ *     host threads at once (the reference's kernel objects are not re-entrant either:
+ *     src/Kernels/ModeCouplingKernels.jl:190-208 mutates its own scratch).
+ *
+ * There is no CPU fallback: without a usable sm_100 device every call returns MCT_CUDA_ERROR.
+ */
+#ifndef MCT_H
+#define MCT_H
+
+#if defined(__GNUC__)
+#define MCT_API __attribute__((visibility("default")))
+#else
+#define MCT_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* status codes and the reference behaviour they map to */
+#define MCT_OK 0
+#define MCT_NOT_CONVERGED 1 /* DomainError("Iteration did not converge...")  src/TimeDoublingSolver.jl:406-408;
+                               error("The recursive iteration did not converge...") src/SteadyStateMemoryEquation.jl:76-78 */
+#define MCT_BAD_ARGUMENT 2  /* @assert on the grid, src/Kernels/ModeCouplingKernels.jl:103-104; size mismatches */
+#define MCT_UNSUPPORTED 3   /* non-Float64, non-diagonal C1 (LinearSolve branch, src/TimeDoublingSolver.jl:73-77,338-344),
+                               custom update_coefficients! (src/MemoryEquation.jl:44), ismutable=false */
+#define MCT_CUDA_ERROR 4    /* CUDA / NCCL failure, or no sm_100 device */
+
+typedef struct mct_kernel_s *mct_kernel_t;     /* replaces a MemoryKernel object (src/Kernels.jl:1) */
+typedef struct mct_equation_s *mct_equation_t; /* a MemoryEquation resident on the device (src/MemoryEquation.jl:23-52) */
+
+MCT_API const char *mct_last_error(void); /* message of the last failing call on this thread */
+MCT_API int mct_device_count(int *count);
+MCT_API int mct_version(void);
+
+/* ---- memory kernels: plug-in point #2, `evaluate_kernel!(out, kernel, F, t)`  src/Kernels.jl:10-26 ---- */
+
+/* ModeCouplingKernel3D from the tables the untouched Julia constructor produced:
+ * kernel.k_array, kernel.V1, kernel.V2, kernel.V3  (src/Kernels/ModeCouplingKernels.jl:2-17, 94-129). */
+MCT_API int mct_sc3d_create(mct_kernel_t *out, int device, int Nk, const double *k_array, const double *V1, const double *V2,
+                    const double *V3);
+/* Same kernel, tables built on the device in the constructor's own operation order (:105-126) -- avoids
+ * shipping 3*Nk^2 doubles over PCIe for packing-fraction sweeps. */
+MCT_API int mct_sc3d_create_from_sk(mct_kernel_t *out, int device, int Nk, double rho, double kBT, double m, const double *k_array,
+                            const double *Sk);
+/* TaggedModeCouplingKernel3D (:265-282, 390-467).  `Fc_traj` is sol.F of the collective solution, [nt][Nk];
+ * the reference's tDict[t] float lookup (:394,:436) becomes the integer index of t in sol.t. */
+MCT_API int mct_sc3d_tagged_create(mct_kernel_t *out, int device, int Nk, const double *k_array, const double *V1, const double *V2,
+                           const double *V3, long nt, const double *Fc_traj);
+MCT_API int mct_sc3d_tagged_create_from_sk(mct_kernel_t *out, int device, int Nk, double rho, double kBT, double m,
+                                   const double *k_array, const double *Sk, long nt, const double *Fc_traj);
+/* Tagged kernel chained on the device-resident trajectory of a finished collective solve (no PCIe round trip). */
+MCT_API int mct_sc3d_tagged_create_from_equation(mct_kernel_t *out, int Nk, double rho, double kBT, double m, const double *k_array,
+                                         const double *Sk, mct_equation_t collective);
+/* MultiComponentModeCouplingKernel3D from kernel.C (Vector{SMatrix}) and kernel.prefactor (Ns x Ns)
+ * (src/Kernels/MultiComponentKernels.jl:45-60, 84-131). */
+MCT_API int mct_mc3d_create(mct_kernel_t *out, int device, int Nk, int Ns, const double *k_array, const double *C,
+                    const double *prefactor);
+/* dDimModeCouplingKernel from kernel.prefactor, kernel.V, kernel.J (Nk x Nk x Nk column-major [iq,ik,ip])
+ * (src/Kernels/ModeCouplingKernels.jl:19-71). */
+MCT_API int mct_ddim_create(mct_kernel_t *out, int device, int Nk, const double *k_array, double prefactor, const double *V,
+                    const double *J);
+/* evaluate_kernel!(out, kernel, F, t): F and out are dof doubles.  t_index is used by tagged kernels only. */
+MCT_API int mct_kernel_eval(mct_kernel_t kernel, const double *F, long t_index, double *out);
+/* n independent evaluations K_b = kernel(F_b), F and out are [n][dof] (parity tests, roofline measurement). */
+MCT_API int mct_kernel_eval_many(mct_kernel_t kernel, int n, const double *F, double *out, float *device_ms);
+MCT_API int mct_kernel_destroy(mct_kernel_t kernel);
+
+/* ---- TimeDoublingSolver: plug-in point #1, `solve(equation, solver)`  src/Solvers.jl:42-46 ---- */
+
+/* keyword arguments of TimeDoublingSolver(; N, Δt, t_max, max_iterations, tolerance, verbose, ismutable,
+ * init_with_memory)  src/TimeDoublingSolver.jl:48-50 */
+typedef struct mct_td_options {
+    int N;
+    double dt;
+    double t_max;
+    long max_iterations;
+    double tolerance;
+    int verbose;
+    int init_with_memory; /* must be 1 (the default); 0 -> MCT_UNSUPPORTED */
+} mct_td_options;
+
+/* MemoryEquationCoefficients after cleaning (src/MemoryEquation.jl:15-21, src/HelperFunctions.jl:73-84):
+ * kind 0 = UniformScaling: pass lambda in *_scalar;  kind 1 = Diagonal: pass `.diag` (Nk doubles for Ns = 1,
+ * Nk blocks of Ns x Ns otherwise).  delta: dof doubles or NULL for zero. */
+typedef struct mct_coeffs {
+    int alpha_kind; double alpha_scalar; const double *alpha;
+    int beta_kind;  double beta_scalar;  const double *beta;
+    int gamma_kind; double gamma_scalar; const double *gamma;
+    const double *delta;
+} mct_coeffs;
+
+/* nt = 1 + 2N + 2N*ceil-count of doublings while dt < 2*t_max  (src/TimeDoublingSolver.jl:518,523-528) */
+MCT_API int mct_td_output_len(const mct_td_options *opts, long *nt);
+
+/* solve(MemoryEquation(alpha,beta,gamma,delta,F0,dF0,kernel), TimeDoublingSolver(opts))
+ * (src/TimeDoublingSolver.jl:512-532).  t_out[nt], F_out[nt][dof], K_out[nt][dof] are caller-allocated;
+ * *kernel_evals receives solver.kernel_evals (:416,:520). */
+MCT_API int mct_td_solve(mct_kernel_t kernel, const mct_coeffs *coeffs, const double *F0, const double *dF0,
+                 const mct_td_options *opts, double *t_out, double *F_out, double *K_out, long *kernel_evals);
+
+/* Device-resident form of the same call: create uploads coefficients/initial conditions and allocates the
+ * history rings + trajectory; solve runs the persistent kernel only (no host<->device traffic); download copies
+ * (t,F,K) back.  mct_td_solve == create + solve + download + destroy. */
+MCT_API int mct_equation_create(mct_equation_t *out, mct_kernel_t kernel, const mct_coeffs *coeffs, const double *F0,
+                        const double *dF0, const mct_td_options *opts);
+MCT_API int mct_equation_solve(mct_equation_t eq, long *kernel_evals, float *device_ms);
+MCT_API int mct_equation_download(mct_equation_t eq, double *t_out, double *F_out, double *K_out);
+MCT_API int mct_equation_destroy(mct_equation_t eq);
+/* Batch of independent equations with identical (Nk, Ns, options) -- e.g. a packing-fraction sweep.  All
+ * equations are solved by ONE persistent launch per device; status[i]/kernel_evals[i] are per equation. */
+MCT_API int mct_equation_solve_batch(int n, mct_equation_t *eqs, int *status, long *kernel_evals, float *device_ms);
+
+/* solve_steady_state(gamma, F0, kernel; tolerance, max_iterations)  src/SteadyStateMemoryEquation.jl:59-100.
+ * gamma: dof doubles (Diagonal / blocks).  F_out, K_out: dof doubles. */
+MCT_API int mct_steady_state(mct_kernel_t kernel, const double *gamma, const double *F0, double tolerance, long max_iterations,
+                     double *F_out, double *K_out, long *iterations);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCT_H */

@@ -1,0 +1,419 @@
+"""Host-side mirror of the reference's interface for the accelerated path.
+
+The reference is Julia (not installed in this image), so the host side that would be the Julia glue
+(`julia/MCTDevice.jl`) is mirrored here in Python with the same names, argument meaning and
+error behaviour, on top of the C ABI of libmct_sm100a.so (include/mct.h):
+
+    ModeCouplingKernel, TaggedModeCouplingKernel           src/Kernels/ModeCouplingKernels.jl:94, :390
+    evaluate_kernel, evaluate_kernel_                       src/Kernels.jl:10-26   (`evaluate_kernel!`)
+    MemoryEquation                                          src/MemoryEquation.jl:44-52
+    TimeDoublingSolver, solve                               src/TimeDoublingSolver.jl:48-50, :512-532
+    solve_steady_state                                      src/SteadyStateMemoryEquation.jl:49-56
+    get_t, get_F, get_K, find_relaxation_time               src/HelperFunctions.jl:169-253, src/RelaxationTime.jl:14-39
+
+Every numerical operation happens on the GPU.  There is no CPU fallback: if the CUDA library is missing or no
+sm_100 device is present the calls raise `MCTDeviceError`.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "lib", "libmct_sm100a.so")
+_lib = None
+
+c_dp = C.POINTER(C.c_double)
+
+MCT_OK, MCT_NOT_CONVERGED, MCT_BAD_ARGUMENT, MCT_UNSUPPORTED, MCT_CUDA_ERROR = 0, 1, 2, 3, 4
+
+
+class MCTDeviceError(RuntimeError):
+    """CUDA failure, missing library or missing B200 (MCT_CUDA_ERROR) -- never silently replaced by a CPU path."""
+
+
+class DomainError(ArithmeticError):
+    """Mirrors Julia's DomainError thrown at src/TimeDoublingSolver.jl:406-408."""
+
+
+class TdOptions(C.Structure):
+    _fields_ = [("N", C.c_int), ("dt", C.c_double), ("t_max", C.c_double), ("max_iterations", C.c_long),
+                ("tolerance", C.c_double), ("verbose", C.c_int), ("init_with_memory", C.c_int)]
+
+
+class Coeffs(C.Structure):
+    _fields_ = [("alpha_kind", C.c_int), ("alpha_scalar", C.c_double), ("alpha", c_dp),
+                ("beta_kind", C.c_int), ("beta_scalar", C.c_double), ("beta", c_dp),
+                ("gamma_kind", C.c_int), ("gamma_scalar", C.c_double), ("gamma", c_dp),
+                ("delta", c_dp)]
+
+
+EXPORTS = [
+    "mct_last_error", "mct_device_count", "mct_version", "mct_sc3d_create", "mct_sc3d_create_from_sk",
+    "mct_sc3d_tagged_create", "mct_sc3d_tagged_create_from_sk", "mct_sc3d_tagged_create_from_equation", "mct_mc3d_create",
+    "mct_ddim_create", "mct_kernel_eval", "mct_kernel_eval_many", "mct_kernel_destroy", "mct_td_output_len", "mct_td_solve",
+    "mct_equation_create", "mct_equation_solve", "mct_equation_download", "mct_equation_destroy", "mct_equation_solve_batch",
+    "mct_steady_state",
+]
+
+
+def library_path():
+    return _LIB_PATH
+
+
+def load_library():
+    """dlopen libmct_sm100a.so (no compute call is made here)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise MCTDeviceError(f"{_LIB_PATH} is missing: run `python __graft_entry__.py build` (there is no CPU fallback)")
+        L = C.CDLL(_LIB_PATH)
+        L.mct_last_error.restype = C.c_char_p
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc == MCT_OK:
+        return
+    msg = load_library().mct_last_error().decode()
+    if rc == MCT_NOT_CONVERGED:
+        raise DomainError(msg)
+    if rc == MCT_BAD_ARGUMENT:
+        raise AssertionError(msg)
+    if rc == MCT_UNSUPPORTED:
+        raise NotImplementedError(msg)
+    raise MCTDeviceError(msg)
+
+
+def _arr(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if shape is not None:
+        a = a.reshape(shape)
+    return a
+
+
+def _p(a):
+    return a.ctypes.data_as(c_dp)
+
+
+def device_count():
+    n = C.c_int(0)
+    _check(load_library().mct_device_count(C.byref(n)))
+    return n.value
+
+
+# --------------------------------------------------------------------------------------------- kernels
+class MemoryKernel:
+    """Opaque device kernel handle (replaces a `MemoryKernel` object, src/Kernels.jl:1)."""
+
+    def __init__(self, handle, Nk, Ns=1, device=0, keep=()):
+        self._h = handle
+        self.Nk, self.Ns, self.device = Nk, Ns, device
+        self._keep = keep
+
+    @property
+    def dof(self):
+        return self.Nk * self.Ns * self.Ns
+
+    def close(self):
+        if self._h is not None and _lib is not None:
+            _lib.mct_kernel_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def vertex_tables(rho, kBT, m, k_array, Sk, tagged=False):
+    """The reference constructor's V1, V2, V3 (Nk x Nk, [iq, ip]) in its own operation order
+    (src/Kernels/ModeCouplingKernels.jl:105-126 collective, :402-422 tagged).  Host-side, like the Julia constructor
+    that stays untouched; the `from_sk` constructors build the same tables on the device instead."""
+    k = _arr(k_array)
+    Sk = _arr(Sk)
+    dk = k[1] - k[0]
+    Ck = (Sk - 1.0) / (rho * Sk)
+    D0 = kBT / m
+    q, p = k[:, None], k[None, :]
+    cq, cp = Ck[:, None], Ck[None, :]
+    dd = q * q - p * p
+    if not tagged:
+        c8 = 8.0 * (np.pi * np.pi)
+        s = cp + cq
+        dc = cq - cp
+        V1 = p * q * (s * s) / 4.0 * D0 * rho / c8 * dk * dk
+        V2 = p * q * (dd * dd) * (dc * dc) / 4.0 * D0 * rho / c8 * dk * dk
+        V3 = p * q * dd * (cq * cq - cp * cp) / 2.0 * D0 * rho / c8 * dk * dk
+    else:
+        c4 = 4.0 * (np.pi * np.pi)
+        dk2 = dk * dk
+        c2 = cq * cq + 0.0 * cp
+        V1 = p * q * c2 / 4.0 * D0 * rho / c4 * dk2
+        V2 = p * q * (dd * dd) * c2 / 4.0 * D0 * rho / c4 * dk2
+        V3 = p * q * dd * c2 / 2.0 * D0 * rho / c4 * dk2
+    return [np.asfortranarray(v) for v in (V1, V2, V3)]
+
+
+def ModeCouplingKernel(rho, kBT, m, k_array, Sk, dims=3, device=0, tables=None):
+    """ModeCouplingKernel(ρ, kBT, m, k_array, Sₖ; dims=3)  -- src/Kernels/ModeCouplingKernels.jl:94-129.
+
+    `tables=(V1, V2, V3)` passes tables made elsewhere (what the Julia glue does with `kernel.V1..V3`); by default
+    the tables are built on the device from S(k)."""
+    if dims != 3:
+        raise NotImplementedError("dDimModeCouplingKernel is not implemented on the device yet")
+    L = load_library()
+    k = _arr(k_array)
+    h = C.c_void_p()
+    if tables is None:
+        Sk = _arr(Sk)
+        _check(L.mct_sc3d_create_from_sk(C.byref(h), device, len(k), C.c_double(rho), C.c_double(kBT), C.c_double(m), _p(k), _p(Sk)))
+    else:
+        V = [np.asfortranarray(v, dtype=np.float64) for v in tables]
+        _check(L.mct_sc3d_create(C.byref(h), device, len(k), _p(k), _p(V[0]), _p(V[1]), _p(V[2])))
+    return MemoryKernel(h, len(k), 1, device)
+
+
+def TaggedModeCouplingKernel(rho, kBT, m, k_array, Sk, sol, dims=3, device=0, tables=None):
+    """TaggedModeCouplingKernel(ρ, kBT, m, k_array, Sₖ, sol; dims=3) -- src/Kernels/ModeCouplingKernels.jl:390-426.
+    `sol` is the collective MemoryEquationSolution; if it still holds its device trajectory the tagged kernel is
+    chained on it without a host round trip."""
+    if dims != 3:
+        raise NotImplementedError("dDimTaggedModeCouplingKernel is not implemented on the device yet")
+    L = load_library()
+    k = _arr(k_array)
+    Sk = _arr(Sk)
+    h = C.c_void_p()
+    if tables is None and getattr(sol, "_equation", None) is not None:
+        _check(L.mct_sc3d_tagged_create_from_equation(C.byref(h), len(k), C.c_double(rho), C.c_double(kBT), C.c_double(m),
+                                                      _p(k), _p(Sk), sol._equation._q))
+        return MemoryKernel(h, len(k), 1, device, keep=(sol._equation,))
+    Fc = _arr(sol.F)
+    if tables is None:
+        _check(L.mct_sc3d_tagged_create_from_sk(C.byref(h), device, len(k), C.c_double(rho), C.c_double(kBT), C.c_double(m),
+                                                _p(k), _p(Sk), C.c_long(Fc.shape[0]), _p(Fc)))
+    else:
+        V = [np.asfortranarray(v, dtype=np.float64) for v in tables]
+        _check(L.mct_sc3d_tagged_create(C.byref(h), device, len(k), _p(k), _p(V[0]), _p(V[1]), _p(V[2]),
+                                        C.c_long(Fc.shape[0]), _p(Fc)))
+    return MemoryKernel(h, len(k), 1, device)
+
+
+def evaluate_kernel(kernel, F, t=0):
+    """out = evaluate_kernel(kernel, F, t) -- src/Kernels.jl:18-26.  For tagged kernels `t` is the index of the time
+    in the collective solution's `t` array."""
+    out = np.empty(kernel.dof)
+    evaluate_kernel_(out, kernel, F, t)
+    return out
+
+
+def evaluate_kernel_(out, kernel, F, t=0):
+    """evaluate_kernel!(out, kernel, F, t) -- src/Kernels.jl:10-16."""
+    F = _arr(F, (kernel.dof,))
+    assert out.dtype == np.float64 and out.flags.c_contiguous and out.size == kernel.dof
+    _check(load_library().mct_kernel_eval(kernel._h, _p(F), C.c_long(int(t)), _p(out)))
+    return out
+
+
+def evaluate_kernel_many(kernel, F):
+    F = _arr(F, (-1, kernel.dof))
+    out = np.empty_like(F)
+    ms = C.c_float(0)
+    _check(load_library().mct_kernel_eval_many(kernel._h, F.shape[0], _p(F), _p(out), C.byref(ms)))
+    return out, ms.value
+
+
+# --------------------------------------------------------------------------------------------- equation + solver
+class MemoryEquation:
+    """MemoryEquation(α, β, γ, δ, F₀, ∂ₜF₀, kernel) -- src/MemoryEquation.jl:44-52.
+
+    α F̈ + β Ḟ + γ F + δ + ∫ K(τ) Ḟ(t-τ) dτ = 0.  Scalars become UniformScaling, vectors become Diagonal
+    (src/HelperFunctions.jl:73-84).  A custom `update_coefficients!` is not supported on the device."""
+
+    def __init__(self, alpha, beta, gamma, delta, F0, dF0, kernel, update_coefficients=None):
+        if update_coefficients is not None:
+            raise NotImplementedError("update_coefficients! callbacks are not supported by the device solver")
+        self.kernel = kernel
+        self.F0 = _arr(F0, (kernel.dof,))
+        self.dF0 = _arr(dF0, (kernel.dof,))
+        self.coeffs = {}
+        for name, v in (("alpha", alpha), ("beta", beta), ("gamma", gamma)):
+            self.coeffs[name] = float(v) if np.isscalar(v) else _arr(v, (kernel.dof,))
+        self.delta = None if (np.isscalar(delta) and float(delta) == 0.0) else (
+            np.full(kernel.dof, float(delta)) if np.isscalar(delta) else _arr(delta, (kernel.dof,)))
+
+    def _c_coeffs(self):
+        c = Coeffs()
+        for name in ("alpha", "beta", "gamma"):
+            v = self.coeffs[name]
+            if isinstance(v, float):
+                setattr(c, name + "_kind", 0); setattr(c, name + "_scalar", v); setattr(c, name, None)
+            else:
+                setattr(c, name + "_kind", 1); setattr(c, name + "_scalar", 0.0); setattr(c, name, _p(v))
+        c.delta = _p(self.delta) if self.delta is not None else None
+        return c
+
+
+class TimeDoublingSolver:
+    """TimeDoublingSolver(; N=32, Δt=1e-10, t_max=1e10, max_iterations=10^4, tolerance=1e-10, verbose=false,
+    ismutable=true, init_with_memory=true) -- src/TimeDoublingSolver.jl:48-50 (Δt is spelled `dt`)."""
+
+    def __init__(self, N=32, dt=1e-10, t_max=1e10, max_iterations=10 ** 4, tolerance=1e-10, verbose=False, ismutable=True,
+                 init_with_memory=True):
+        if not ismutable:
+            raise NotImplementedError("ismutable=false is not supported by the device solver")
+        self.N, self.dt, self.t_max = int(N), float(dt), float(t_max)
+        self.max_iterations, self.tolerance = int(max_iterations), float(tolerance)
+        self.verbose, self.init_with_memory = bool(verbose), bool(init_with_memory)
+        self.kernel_evals = 0
+        self.device_ms = None
+
+    def _c_opts(self):
+        return TdOptions(self.N, self.dt, self.t_max, self.max_iterations, self.tolerance, int(self.verbose),
+                         int(self.init_with_memory))
+
+    def output_len(self):
+        nt = C.c_long(0)
+        o = self._c_opts()
+        _check(load_library().mct_td_output_len(C.byref(o), C.byref(nt)))
+        return nt.value
+
+
+class _DeviceEquation:
+    def __init__(self, q):
+        self._q = q
+
+    def close(self):
+        if self._q is not None and _lib is not None:
+            _lib.mct_equation_destroy(self._q)
+            self._q = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class MemoryEquationSolution:
+    """MemoryEquationSolution(t, F, K, solver) -- src/Solvers.jl:19-24.  F and K are [nt, dof] arrays: row `it` is the
+    reference's `sol.F[it]` (and the diagonal of `sol.K[it]`)."""
+
+    def __init__(self, t, F, K, solver, equation=None):
+        self.t, self.F, self.K, self.solver = t, F, K, solver
+        self._equation = equation
+
+    def __getitem__(self, ik):   # getindex(sol, I...) = getindex.(sol.F, I...)  src/Solvers.jl:50
+        return self.F[:, ik]
+
+
+def get_t(sol):
+    return sol.t
+
+
+def get_F(sol, *idx):
+    return sol.F[idx] if idx else sol.F
+
+
+def get_K(sol, *idx):
+    return sol.K[idx] if idx else sol.K
+
+
+def _create_equation(equation, solver):
+    L = load_library()
+    q = C.c_void_p()
+    c = equation._c_coeffs()
+    o = solver._c_opts()
+    _check(L.mct_equation_create(C.byref(q), equation.kernel._h, C.byref(c), _p(equation.F0), _p(equation.dF0), C.byref(o)))
+    return _DeviceEquation(q)
+
+
+def _download(dev_eq, solver, dof, keep_device):
+    L = load_library()
+    nt = solver.output_len()
+    t = np.empty(nt); F = np.empty((nt, dof)); K = np.empty((nt, dof))
+    _check(L.mct_equation_download(dev_eq._q, _p(t), _p(F), _p(K)))
+    return MemoryEquationSolution(t, F, K, solver, dev_eq if keep_device else None)
+
+
+def solve(equation, solver=None, keep_device=True):
+    """solve(equation, solver) -- src/Solvers.jl:42-46, src/TimeDoublingSolver.jl:512-532.
+    Writes solver.kernel_evals like the reference (:416, :520)."""
+    solver = solver or TimeDoublingSolver()
+    L = load_library()
+    dev_eq = _create_equation(equation, solver)
+    evals = C.c_long(0)
+    ms = C.c_float(0)
+    rc = L.mct_equation_solve(dev_eq._q, C.byref(evals), C.byref(ms))
+    solver.kernel_evals = evals.value
+    solver.device_ms = ms.value
+    _check(rc)
+    sol = _download(dev_eq, solver, equation.kernel.dof, keep_device)
+    if not keep_device:
+        dev_eq.close()
+    return sol
+
+
+def solve_batch(equations, solver=None, download=True):
+    """Many independent equations with identical (Nk, solver options) in ONE persistent launch
+    (e.g. a packing-fraction sweep).  Returns (solutions, statuses, kernel_evals, device_ms)."""
+    solver = solver or TimeDoublingSolver()
+    L = load_library()
+    devs = [_create_equation(e, solver) for e in equations]
+    n = len(devs)
+    arr = (C.c_void_p * n)(*[d._q for d in devs])
+    status = (C.c_int * n)()
+    evals = (C.c_long * n)()
+    ms = C.c_float(0)
+    rc = L.mct_equation_solve_batch(n, arr, status, evals, C.byref(ms))
+    if rc not in (MCT_OK, MCT_NOT_CONVERGED):
+        _check(rc)
+    sols = []
+    if download:
+        for d, e in zip(devs, equations):
+            sols.append(_download(d, solver, e.kernel.dof, False))
+    for d in devs:
+        d.close()
+    solver.kernel_evals = int(sum(evals))
+    solver.device_ms = ms.value
+    return sols, list(status), list(evals), ms.value
+
+
+def solve_steady_state(gamma, F0, kernel, tolerance=1e-8, max_iterations=10 ** 6, verbose=False):
+    """solve_steady_state(γ, F₀, kernel; tolerance, max_iterations) -- src/SteadyStateMemoryEquation.jl:49-100."""
+    g = _arr(gamma, (kernel.dof,)) if not np.isscalar(gamma) else np.full(kernel.dof, float(gamma))
+    F0 = _arr(F0, (kernel.dof,))
+    F = np.empty(kernel.dof); K = np.empty(kernel.dof)
+    it = C.c_long(0)
+    rc = load_library().mct_steady_state(kernel._h, _p(g), _p(F0), C.c_double(tolerance), C.c_long(max_iterations), _p(F), _p(K),
+                                         C.byref(it))
+    if rc == MCT_NOT_CONVERGED:
+        raise RuntimeError(load_library().mct_last_error().decode())   # `error(...)` :76-78
+    _check(rc)
+    sol = MemoryEquationSolution(np.array([np.inf]), F[None, :], K[None, :],
+                                 dict(tolerance=tolerance, max_iterations=max_iterations, verbose=verbose))
+    sol.iterations = it.value
+    return sol
+
+
+def find_relaxation_time(t, F, threshold=np.exp(-1), mode="log"):
+    """find_relaxation_time(t, F; threshold=exp(-1), mode=:log) -- src/RelaxationTime.jl:14-39 (O(nt) host
+    post-processing of a finished solution, kept on the host like in the reference)."""
+    t = np.asarray(t, dtype=np.float64)
+    F = np.asarray(F, dtype=np.float64)
+    for it in range(len(t)):
+        if F[it] / F[0] > threshold:
+            continue
+        if it == 0:
+            return 0.0
+        y0, y1, y = F[it] / F[0], F[it - 1] / F[0], threshold
+        if mode == "log":
+            x0, x1 = np.log(t[it]), np.log(t[it - 1])
+            return float(np.exp(((y - y0) * (x1 - x0) + x0 * (y1 - y0)) / (y1 - y0)))
+        if mode == "lin":
+            x0, x1 = t[it], t[it - 1]
+            return float(((y - y0) * (x1 - x0) + x0 * (y1 - y0)) / (y1 - y0))
+        raise ValueError(f"the mode ':{mode}' is not know. it must be either :lin, :log.")
+    return float("inf")

@@ -1,0 +1,659 @@
+// abi.cu -- the extern "C" boundary declared in include/mct.h.
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <tuple>
+
+#include "common.cuh"
+#include "eval.cuh"
+#include "layout.cuh"
+#include "td_sc.cuh"
+
+namespace mct {
+
+static thread_local std::string g_last_error;
+void set_error(const std::string &msg) { g_last_error = msg; }
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
+    char buf[512];
+    snprintf(buf, sizeof(buf), "CUDA error %d (%s) in %s at %s:%d", (int)e, cudaGetErrorString(e), what, file, line);
+    g_last_error = buf;
+    return MCT_CUDA_ERROR;
+}
+
+enum KernelType { K_SC3D = 1, K_TAGGED3D = 2, K_MC3D = 3, K_DDIM = 5 };
+
+// geometry of a team layout is shared by every kernel handle with the same (device, Nk, G, sym, smem_terms)
+using GeomKey = std::tuple<int, int, int, int, int>;
+static std::mutex g_geom_mutex;
+static std::map<GeomKey, TeamLayout *> g_geoms;
+
+}  // namespace mct
+
+using namespace mct;
+
+struct mct_kernel_s {
+    int type = 0, device = 0, Nk = 0, Ns = 1, sym = 0;
+    cudaStream_t stream = nullptr;
+    double *d_k = nullptr, *d_V1 = nullptr, *d_V2 = nullptr, *d_V3 = nullptr;  // raw column-major tables (may be absent)
+    // S(k)-defined kernels keep what is needed to rebuild tables in any layout
+    bool from_sk = false;
+    double rho = 0, kBT = 0, m = 0;
+    double *d_Sk = nullptr, *d_Ck = nullptr;
+    // tagged
+    long nt = 0;
+    double *d_Fc = nullptr;
+    bool owns_Fc = false;
+    std::map<TeamLayout *, double *> slabs;  // team-layout tables per geometry
+    double *d_scratch = nullptr; size_t scratch_doubles = 0;
+    double *d_io = nullptr; size_t io_doubles = 0;
+    int n_sm = 0; size_t smem_optin = 0;
+};
+
+struct mct_equation_s {
+    mct_kernel_t kernel = nullptr;
+    int Nk = 0, nblocks = 0, second_order = 0, mode = 0;
+    long nt = 0;
+    mct_td_options opts{};
+    double *d_coef = nullptr;   // alpha, beta, gamma, delta, F0, dF0  [6][Nk]
+    double *d_ring = nullptr, *d_F = nullptr, *d_K = nullptr;
+    int *d_status = nullptr;
+    long long *d_evals = nullptr;
+    bool solved = false;
+};
+
+namespace mct {
+
+static int ensure_scratch(mct_kernel_t h, size_t doubles) {
+    if (h->scratch_doubles >= doubles) return MCT_OK;
+    cudaFree(h->d_scratch);
+    h->d_scratch = nullptr; h->scratch_doubles = 0;
+    MCT_CUDA(cudaMalloc(&h->d_scratch, doubles * sizeof(double)));
+    h->scratch_doubles = doubles;
+    return MCT_OK;
+}
+static int ensure_io(mct_kernel_t h, size_t doubles) {
+    if (h->io_doubles >= doubles) return MCT_OK;
+    cudaFree(h->d_io);
+    h->d_io = nullptr; h->io_doubles = 0;
+    MCT_CUDA(cudaMalloc(&h->d_io, doubles * sizeof(double)));
+    h->io_doubles = doubles;
+    return MCT_OK;
+}
+
+static bool approx(double a, double b) {  // Julia isapprox default: rtol = sqrt(eps)
+    return std::fabs(a - b) <= 1.4901161193847656e-08 * std::max(std::fabs(a), std::fabs(b));
+}
+
+// @assert k_array[1] ≈ Δk/2 ; @assert all(diff(k_array) .≈ Δk)   src/Kernels/ModeCouplingKernels.jl:103-104
+static int check_grid(int Nk, const double *k) {
+    MCT_REQUIRE(Nk >= 2, MCT_BAD_ARGUMENT, "k_array needs at least two points");
+    MCT_REQUIRE(k != nullptr, MCT_BAD_ARGUMENT, "k_array is NULL");
+    const double dk = k[1] - k[0];
+    MCT_REQUIRE(approx(k[0], dk / 2), MCT_BAD_ARGUMENT, "grid assertion failed: k_array[1] must equal dk/2");
+    for (int i = 1; i < Nk; i++)
+        MCT_REQUIRE(approx(k[i] - k[i - 1], dk), MCT_BAD_ARGUMENT, "grid assertion failed: k_array must be equidistant");
+    return MCT_OK;
+}
+
+static int new_handle(mct_kernel_t *out, int type, int device, int Nk, const double *k) {
+    MCT_REQUIRE(out != nullptr, MCT_BAD_ARGUMENT, "output handle pointer is NULL");
+    *out = nullptr;
+    int rc = check_grid(Nk, k);
+    if (rc) return rc;
+    int ndev = 0;
+    MCT_CUDA(cudaGetDeviceCount(&ndev));
+    MCT_REQUIRE(device >= 0 && device < ndev, MCT_BAD_ARGUMENT, "no such CUDA device");
+    MCT_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    MCT_CUDA(cudaGetDeviceProperties(&prop, device));
+    MCT_REQUIRE(prop.major == 10, MCT_CUDA_ERROR, "libmct_sm100a needs an sm_100 (B200) device; there is no CPU or other-GPU fallback");
+    mct_kernel_t h = new mct_kernel_s();
+    h->type = type; h->device = device; h->Nk = Nk;
+    h->n_sm = prop.multiProcessorCount; h->smem_optin = prop.sharedMemPerBlockOptin;
+    cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_k, Nk * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h->d_k, k, Nk * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+    if (e != cudaSuccess) { delete h; return cuda_fail(e, "new_handle", __FILE__, __LINE__); }
+    *out = h;
+    return MCT_OK;
+}
+
+static int upload_tables(mct_kernel_t h, const double *V1, const double *V2, const double *V3) {
+    const size_t n2 = (size_t)h->Nk * h->Nk;
+    MCT_REQUIRE(V1 && V2 && V3, MCT_BAD_ARGUMENT, "vertex table pointer is NULL");
+    MCT_CUDA(cudaMalloc(&h->d_V1, 3 * n2 * sizeof(double)));
+    h->d_V2 = h->d_V1 + n2; h->d_V3 = h->d_V2 + n2;
+    MCT_CUDA(cudaMemcpyAsync(h->d_V1, V1, n2 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    MCT_CUDA(cudaMemcpyAsync(h->d_V2, V2, n2 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    MCT_CUDA(cudaMemcpyAsync(h->d_V3, V3, n2 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    return MCT_OK;
+}
+
+static bool tables_symmetric(int Nk, const double *V1, const double *V2, const double *V3) {
+    for (int a = 0; a < Nk; a++)
+        for (int b = a + 1; b < Nk; b++) {
+            size_t x = (size_t)a + (size_t)b * Nk, y = (size_t)b + (size_t)a * Nk;
+            if (V1[x] != V1[y] || V2[x] != V2[y] || V3[x] != V3[y]) return false;
+        }
+    return true;
+}
+
+static int ensure_raw_tables(mct_kernel_t h) {
+    if (h->d_V1) return MCT_OK;
+    MCT_REQUIRE(h->from_sk, MCT_BAD_ARGUMENT, "kernel has no tables");
+    const size_t n2 = (size_t)h->Nk * h->Nk;
+    MCT_CUDA(cudaMalloc(&h->d_V1, 3 * n2 * sizeof(double)));
+    h->d_V2 = h->d_V1 + n2; h->d_V3 = h->d_V2 + n2;
+    return tables_from_sk(h->Nk, h->d_k, h->d_Sk, h->d_Ck, h->rho, h->kBT, h->m, h->type == K_TAGGED3D, h->d_V1, h->d_V2, h->d_V3,
+                          h->stream);
+}
+
+static int setup_from_sk(mct_kernel_t h, double rho, double kBT, double m, const double *Sk) {
+    MCT_REQUIRE(Sk != nullptr, MCT_BAD_ARGUMENT, "Sk is NULL");
+    h->from_sk = true; h->rho = rho; h->kBT = kBT; h->m = m;
+    MCT_CUDA(cudaMalloc(&h->d_Sk, 2 * (size_t)h->Nk * sizeof(double)));
+    h->d_Ck = h->d_Sk + h->Nk;
+    MCT_CUDA(cudaMemcpyAsync(h->d_Sk, Sk, h->Nk * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    return tables_from_sk(h->Nk, h->d_k, h->d_Sk, h->d_Ck, rho, kBT, m, h->type == K_TAGGED3D, nullptr, nullptr, nullptr, h->stream);
+}
+
+static int upload_traj(mct_kernel_t h, long nt, const double *Fc) {
+    MCT_REQUIRE(nt >= 1 && Fc != nullptr, MCT_BAD_ARGUMENT, "tagged kernel needs the collective trajectory");
+    h->nt = nt; h->owns_Fc = true;
+    MCT_CUDA(cudaMalloc(&h->d_Fc, (size_t)nt * h->Nk * sizeof(double)));
+    MCT_CUDA(cudaMemcpyAsync(h->d_Fc, Fc, (size_t)nt * h->Nk * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    return MCT_OK;
+}
+
+// ---- team geometry selection ------------------------------------------------------------------------------
+static long long total_terms_of(int Nk, int sym) {
+    long long t = 0;
+    for (int ik = 1; ik <= Nk; ik++) {
+        int d = ik - 1;
+        if (sym) t += (Nk - d) + (ik - 1) / 2 + (ik % 2 == 0 ? 1 : 0);
+        else t += (long long)(Nk - d) * (d > 0 ? 2 : 1) + (ik - 1);
+    }
+    return t;
+}
+
+static int env_int(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
+// Returns the (cached) geometry for n_eq concurrent equations on this kernel's device.
+static int choose_geometry(mct_kernel_t h, int n_eq, TeamLayout **out, int *nteams_out) {
+    const int Nk = h->Nk, sym = h->sym;
+    const int n_sm = h->n_sm;
+    const long long total = total_terms_of(Nk, sym);
+    const int target_terms = env_int("MCT_TARGET_TERMS", 4096);
+    // capacity of one CTA: ~ (opt-in shared memory - fixed arrays) / 24 bytes per term
+    const size_t fixed_guess = (size_t)(3 + 3) * (Nk + 2) * 8 + 24 * 1024;
+    const long long cap_guess = h->smem_optin > fixed_guess ? (long long)((h->smem_optin - fixed_guess) / 24) : 1024;
+    int G_fit = (int)std::min<long long>(n_sm, std::max<long long>(1, (total + cap_guess - 1) / cap_guess));
+    int G_lat = (int)std::min<long long>(n_sm, std::max<long long>(1, (total + target_terms - 1) / target_terms));
+    int nteams = std::max(1, std::min(n_eq, n_sm / G_fit));
+    int G = std::max(G_fit, std::min(G_lat, n_sm / nteams));
+    G = std::min(G, n_sm);
+    const int forced = env_int("MCT_TEAM_SIZE", 0);
+    if (forced > 0) G = std::min(forced, n_sm);
+    while ((Nk + G - 1) / G > kThreads) G++;   // at most one row per thread in the row-sum phase
+    nteams = std::max(1, std::min(n_eq, n_sm / G));
+
+    // probe geometry (no spill) to learn slot/task counts and the longest slab, then size the resident part
+    TeamLayout probe;
+    int rc = layout_build_geometry(probe, Nk, G, sym, 1 << 30);
+    if (rc) return rc;
+    long long max_len = 0;
+    for (int c = 0; c < G; c++) max_len = std::max(max_len, probe.cta_off[c + 1] - probe.cta_off[c]);
+    const int slots_b = probe.slots_max + kWarps + 2, tasks_b = probe.tasks_max + 2;
+    const int rows_max = probe.rows_max;
+    layout_free(probe);
+    int cap = td_sc_max_smem_terms(Nk, G, slots_b, tasks_b, rows_max, h->smem_optin);
+    MCT_REQUIRE(cap > 0, MCT_UNSUPPORTED, "shared memory too small for this Nk");
+    const int smem_terms = (int)std::min<long long>(cap, (max_len + 1) / 2 * 2);
+
+    std::lock_guard<std::mutex> lock(g_geom_mutex);
+    GeomKey key(h->device, Nk, G, sym, smem_terms);
+    auto it = g_geoms.find(key);
+    if (it == g_geoms.end()) {
+        TeamLayout *L = new TeamLayout();
+        rc = layout_build_geometry(*L, Nk, G, sym, smem_terms);
+        if (rc) { delete L; return rc; }
+        it = g_geoms.emplace(key, L).first;
+    }
+    *out = it->second;
+    *nteams_out = nteams;
+    return MCT_OK;
+}
+
+static int ensure_slab(mct_kernel_t h, TeamLayout *L, const double **tab) {
+    auto it = h->slabs.find(L);
+    if (it != h->slabs.end()) { *tab = it->second; return MCT_OK; }
+    double *d = nullptr;
+    MCT_CUDA(cudaMalloc(&d, 3 * (size_t)L->total_terms * sizeof(double)));
+    MCT_CUDA(cudaMemsetAsync(d, 0, 3 * (size_t)L->total_terms * sizeof(double), h->stream));
+    int rc;
+    if (h->d_V1) rc = layout_fill_from_tables(*L, d, h->d_V1, h->d_V2, h->d_V3, h->stream);
+    else rc = layout_fill_from_sk(*L, d, h->d_k, h->d_Ck, h->rho, h->kBT, h->m, h->type == K_TAGGED3D, h->stream);
+    if (rc) { cudaFree(d); return rc; }
+    h->slabs[L] = d;
+    *tab = d;
+    return MCT_OK;
+}
+
+static int count_blocks(const mct_td_options *o) {
+    int n = 0;
+    double dt = o->dt;
+    while (dt < o->t_max * 2.0) { n++; dt *= 2.0; }   // src/TimeDoublingSolver.jl:523
+    return n;
+}
+
+static int expand_coef(int kind, double lam, const double *arr, int Nk, double *dst, const char *name) {
+    if (kind == 0) { for (int i = 0; i < Nk; i++) dst[i] = lam; return MCT_OK; }
+    MCT_REQUIRE(kind == 1 && arr != nullptr, MCT_BAD_ARGUMENT, std::string("bad coefficient ") + name);
+    memcpy(dst, arr, Nk * sizeof(double));
+    return MCT_OK;
+}
+
+// One persistent launch for a batch of equations that share kernel geometry and solver options.
+static int run_batch(int n, mct_equation_t *eqs, int mode, double tol, long long max_iter, int *status, long long *evals,
+                     float *device_ms) {
+    MCT_REQUIRE(n >= 1 && eqs != nullptr, MCT_BAD_ARGUMENT, "empty batch");
+    mct_kernel_t h0 = eqs[0]->kernel;
+    MCT_CUDA(cudaSetDevice(h0->device));
+    for (int i = 0; i < n; i++) {
+        mct_kernel_t h = eqs[i]->kernel;
+        MCT_REQUIRE(h->device == h0->device && h->Nk == h0->Nk && h->sym == h0->sym, MCT_BAD_ARGUMENT,
+                    "equations of a batch must share device, Nk and table symmetry");
+        MCT_REQUIRE(h->type == K_SC3D || h->type == K_TAGGED3D, MCT_UNSUPPORTED, "kernel type not supported by this solver");
+        if (mode == 0) {
+            MCT_REQUIRE(eqs[i]->opts.N == eqs[0]->opts.N && eqs[i]->opts.dt == eqs[0]->opts.dt && eqs[i]->nblocks == eqs[0]->nblocks &&
+                            eqs[i]->second_order == eqs[0]->second_order,
+                        MCT_BAD_ARGUMENT, "equations of a batch must share the solver options");
+        }
+    }
+    TeamLayout *L = nullptr;
+    int nteams = 1;
+    int rc = choose_geometry(h0, n, &L, &nteams);
+    if (rc) return rc;
+    cudaStream_t s = h0->stream;
+    std::vector<EqDev> eh(n);
+    for (int i = 0; i < n; i++) {
+        mct_equation_t q = eqs[i];
+        mct_kernel_t h = q->kernel;
+        MCT_CUDA(cudaStreamSynchronize(h->stream));   // uploads of this handle
+        const double *tab = nullptr;
+        rc = ensure_slab(h, L, &tab);
+        if (rc) return rc;
+        MCT_CUDA(cudaStreamSynchronize(h->stream));
+        const int Nk = q->Nk;
+        EqDev &e = eh[i];
+        e.tab = tab; e.kvec = h->d_k;
+        e.alpha = q->d_coef; e.beta = q->d_coef + Nk; e.gamma = q->d_coef + 2 * Nk; e.delta = q->d_coef + 3 * Nk;
+        e.F0 = q->d_coef + 4 * Nk; e.dF0 = q->d_coef + 5 * Nk;
+        e.ring = q->d_ring; e.F_out = q->d_F; e.K_out = q->d_K;
+        e.Fc_traj = (h->type == K_TAGGED3D) ? h->d_Fc : nullptr;
+        e.mode = mode;
+        e.status = q->d_status; e.kernel_evals = q->d_evals;
+    }
+    SolveParams P{};
+    P.Nk = h0->Nk; P.G = L->G; P.N = eqs[0]->opts.N; P.nblocks = eqs[0]->nblocks; P.n_eq = n; P.nteams = nteams;
+    P.second_order = eqs[0]->second_order;
+    P.dt0 = eqs[0]->opts.dt; P.tol = tol; P.max_iter = max_iter;
+    P.total_terms = L->total_terms; P.cta_off = L->d_cta_off; P.tasks = L->d_tasks; P.task_begin = L->d_task_begin;
+    P.rows = L->d_rows; P.row_slot = L->d_row_slot;
+    P.rows_max = L->rows_max; P.slots_max = L->slots_max; P.tasks_max = std::max(1, L->tasks_max); P.smem_terms = L->smem_terms;
+    P.xstride = 3 * ((P.Nk + 1) & ~1) + 16;
+    P.spin_limit_cycles = (long long)env_int("MCT_SPIN_LIMIT_MS", 2000) * 2000000LL;
+
+    // communication scratch: exchange buffers, barrier flags, queue, abort flag, equation table
+    const size_t xbytes = (size_t)nteams * 2 * P.xstride * sizeof(double);
+    const size_t fbytes = (size_t)nteams * P.G * kFlagStride * sizeof(unsigned long long);
+    const size_t ebytes = (size_t)n * sizeof(EqDev);
+    unsigned char *comm = nullptr;
+    const size_t total = xbytes + fbytes + 256 + ebytes;
+    MCT_CUDA(cudaMalloc(&comm, total));
+    cudaError_t ce = cudaMemsetAsync(comm, 0, total, s);
+    P.xbuf = (double *)comm;
+    P.flags = (unsigned long long *)(comm + xbytes);
+    P.queue = (int *)(comm + xbytes + fbytes);
+    P.abort_flag = P.queue + 32;
+    EqDev *d_eqs = (EqDev *)(comm + xbytes + fbytes + 256);
+    P.eqs = d_eqs;
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_eqs, eh.data(), ebytes, cudaMemcpyHostToDevice, s);
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (ce == cudaSuccess) ce = cudaEventCreate(&ev0);
+    if (ce == cudaSuccess) ce = cudaEventCreate(&ev1);
+    if (ce == cudaSuccess) ce = cudaEventRecord(ev0, s);
+    if (ce == cudaSuccess) {
+        rc = td_sc_launch(P, s);
+        if (rc == MCT_OK) {
+            ce = cudaEventRecord(ev1, s);
+            if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+            float ms = 0.f;
+            if (ce == cudaSuccess) ce = cudaEventElapsedTime(&ms, ev0, ev1);
+            if (device_ms) *device_ms = ms;
+        }
+    }
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    if (ce != cudaSuccess) { cudaFree(comm); return cuda_fail(ce, "run_batch", __FILE__, __LINE__); }
+    if (rc != MCT_OK) { cudaFree(comm); return rc; }
+    int worst = MCT_OK;
+    for (int i = 0; i < n; i++) {
+        int st = 0; long long ev = 0;
+        MCT_CUDA(cudaMemcpy(&st, eqs[i]->d_status, sizeof(int), cudaMemcpyDeviceToHost));
+        MCT_CUDA(cudaMemcpy(&ev, eqs[i]->d_evals, sizeof(long long), cudaMemcpyDeviceToHost));
+        if (status) status[i] = st;
+        if (evals) evals[i] = ev;
+        eqs[i]->solved = (st == MCT_OK);
+        if (st != MCT_OK && worst == MCT_OK) worst = st;
+    }
+    cudaFree(comm);
+    if (worst == MCT_NOT_CONVERGED)
+        set_error("Iteration did not converge. Either increase the number of time steps before a time doubling, or choose a "
+                  "different memory kernel.");
+    else if (worst == MCT_CUDA_ERROR) set_error("persistent solver aborted (team barrier timeout)");
+    return worst;
+}
+
+}  // namespace mct
+
+// ================================================ extern "C" ================================================
+extern "C" {
+
+const char *mct_last_error(void) { return g_last_error.c_str(); }
+int mct_version(void) { return 100; }
+
+int mct_device_count(int *count) {
+    MCT_REQUIRE(count != nullptr, MCT_BAD_ARGUMENT, "count is NULL");
+    *count = 0;
+    MCT_CUDA(cudaGetDeviceCount(count));
+    return MCT_OK;
+}
+
+int mct_sc3d_create(mct_kernel_t *out, int device, int Nk, const double *k_array, const double *V1, const double *V2,
+                    const double *V3) {
+    int rc = new_handle(out, K_SC3D, device, Nk, k_array);
+    if (rc) return rc;
+    rc = upload_tables(*out, V1, V2, V3);
+    if (rc) { mct_kernel_destroy(*out); *out = nullptr; return rc; }
+    (*out)->sym = tables_symmetric(Nk, V1, V2, V3) ? 1 : 0;
+    return MCT_OK;
+}
+
+int mct_sc3d_create_from_sk(mct_kernel_t *out, int device, int Nk, double rho, double kBT, double m, const double *k_array,
+                            const double *Sk) {
+    int rc = new_handle(out, K_SC3D, device, Nk, k_array);
+    if (rc) return rc;
+    (*out)->sym = 1;   // the collective vertices are bitwise symmetric under p <-> q (:122-124)
+    rc = setup_from_sk(*out, rho, kBT, m, Sk);
+    if (rc) { mct_kernel_destroy(*out); *out = nullptr; }
+    return rc;
+}
+
+int mct_sc3d_tagged_create(mct_kernel_t *out, int device, int Nk, const double *k_array, const double *V1, const double *V2,
+                           const double *V3, long nt, const double *Fc_traj) {
+    int rc = new_handle(out, K_TAGGED3D, device, Nk, k_array);
+    if (rc) return rc;
+    rc = upload_tables(*out, V1, V2, V3);
+    if (!rc) rc = upload_traj(*out, nt, Fc_traj);
+    if (rc) { mct_kernel_destroy(*out); *out = nullptr; }
+    return rc;
+}
+
+int mct_sc3d_tagged_create_from_sk(mct_kernel_t *out, int device, int Nk, double rho, double kBT, double m,
+                                   const double *k_array, const double *Sk, long nt, const double *Fc_traj) {
+    int rc = new_handle(out, K_TAGGED3D, device, Nk, k_array);
+    if (rc) return rc;
+    rc = setup_from_sk(*out, rho, kBT, m, Sk);
+    if (!rc) rc = upload_traj(*out, nt, Fc_traj);
+    if (rc) { mct_kernel_destroy(*out); *out = nullptr; }
+    return rc;
+}
+
+int mct_sc3d_tagged_create_from_equation(mct_kernel_t *out, int Nk, double rho, double kBT, double m, const double *k_array,
+                                         const double *Sk, mct_equation_t collective) {
+    MCT_REQUIRE(collective && collective->solved && collective->mode == 0, MCT_BAD_ARGUMENT,
+                "collective equation must be solved before a tagged kernel is chained on it");
+    MCT_REQUIRE(collective->Nk == Nk, MCT_BAD_ARGUMENT, "collective solution has a different Nk");
+    int rc = new_handle(out, K_TAGGED3D, collective->kernel->device, Nk, k_array);
+    if (rc) return rc;
+    rc = setup_from_sk(*out, rho, kBT, m, Sk);
+    if (rc) { mct_kernel_destroy(*out); *out = nullptr; return rc; }
+    (*out)->nt = collective->nt; (*out)->d_Fc = collective->d_F; (*out)->owns_Fc = false;
+    return MCT_OK;
+}
+
+int mct_mc3d_create(mct_kernel_t *, int, int, int, const double *, const double *, const double *) {
+    set_error("MultiComponentModeCouplingKernel3D is not implemented on the device yet");
+    return MCT_UNSUPPORTED;
+}
+int mct_ddim_create(mct_kernel_t *, int, int, const double *, double, const double *, const double *) {
+    set_error("dDimModeCouplingKernel is not implemented on the device yet");
+    return MCT_UNSUPPORTED;
+}
+
+int mct_kernel_destroy(mct_kernel_t h) {
+    if (!h) return MCT_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    cudaFree(h->d_k); cudaFree(h->d_V1); cudaFree(h->d_Sk);
+    if (h->owns_Fc) cudaFree(h->d_Fc);
+    for (auto &kv : h->slabs) cudaFree(kv.second);
+    cudaFree(h->d_scratch); cudaFree(h->d_io);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return MCT_OK;
+}
+
+int mct_kernel_eval_many(mct_kernel_t h, int n, const double *F, double *out, float *device_ms) {
+    MCT_REQUIRE(h && F && out && n >= 1, MCT_BAD_ARGUMENT, "bad argument to mct_kernel_eval_many");
+    MCT_REQUIRE(h->type == K_SC3D, MCT_UNSUPPORTED, "mct_kernel_eval_many supports the collective single-component kernel");
+    MCT_CUDA(cudaSetDevice(h->device));
+    int rc = ensure_raw_tables(h);
+    if (rc) return rc;
+    const int Nk = h->Nk;
+    rc = ensure_scratch(h, sc3d_eval_scratch_doubles(Nk, n));
+    if (!rc) rc = ensure_io(h, (size_t)2 * n * Nk);
+    if (rc) return rc;
+    double *dF = h->d_io, *dO = h->d_io + (size_t)n * Nk;
+    MCT_CUDA(cudaMemcpyAsync(dF, F, (size_t)n * Nk * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    cudaEvent_t e0, e1;
+    MCT_CUDA(cudaEventCreate(&e0)); MCT_CUDA(cudaEventCreate(&e1));
+    MCT_CUDA(cudaEventRecord(e0, h->stream));
+    rc = sc3d_eval_launch(Nk, n, h->d_k, h->d_V1, h->d_V2, h->d_V3, dF, Nk, dF, h->d_scratch, dO, h->stream);
+    MCT_CUDA(cudaEventRecord(e1, h->stream));
+    if (rc) return rc;
+    MCT_CUDA(cudaMemcpyAsync(out, dO, (size_t)n * Nk * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    MCT_CUDA(cudaStreamSynchronize(h->stream));
+    float ms = 0.f;
+    MCT_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    if (device_ms) *device_ms = ms;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return MCT_OK;
+}
+
+int mct_kernel_eval(mct_kernel_t h, const double *F, long t_index, double *out) {
+    MCT_REQUIRE(h && F && out, MCT_BAD_ARGUMENT, "bad argument to mct_kernel_eval");
+    MCT_REQUIRE(h->type == K_SC3D || h->type == K_TAGGED3D, MCT_UNSUPPORTED, "kernel type not implemented on the device yet");
+    MCT_CUDA(cudaSetDevice(h->device));
+    int rc = ensure_raw_tables(h);
+    if (rc) return rc;
+    const int Nk = h->Nk;
+    rc = ensure_scratch(h, sc3d_eval_scratch_doubles(Nk, 1));
+    if (!rc) rc = ensure_io(h, (size_t)2 * Nk);
+    if (rc) return rc;
+    double *dF = h->d_io, *dO = h->d_io + Nk;
+    MCT_CUDA(cudaMemcpyAsync(dF, F, Nk * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    const double *dF1 = dF;
+    if (h->type == K_TAGGED3D) {
+        MCT_REQUIRE(t_index >= 0 && t_index < h->nt, MCT_BAD_ARGUMENT, "t is not a time of the collective solution (tDict KeyError)");
+        dF1 = h->d_Fc + (size_t)t_index * Nk;
+    }
+    rc = sc3d_eval_launch(Nk, 1, h->d_k, h->d_V1, h->d_V2, h->d_V3, dF1, 0, dF, h->d_scratch, dO, h->stream);
+    if (rc) return rc;
+    MCT_CUDA(cudaMemcpyAsync(out, dO, Nk * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    MCT_CUDA(cudaStreamSynchronize(h->stream));
+    return MCT_OK;
+}
+
+int mct_td_output_len(const mct_td_options *o, long *nt) {
+    MCT_REQUIRE(o && nt, MCT_BAD_ARGUMENT, "NULL argument");
+    MCT_REQUIRE(o->N >= 1 && o->dt > 0 && o->t_max > 0, MCT_BAD_ARGUMENT, "bad solver options");
+    *nt = 1 + 2L * o->N + 2L * o->N * count_blocks(o);
+    return MCT_OK;
+}
+
+int mct_equation_create(mct_equation_t *out, mct_kernel_t h, const mct_coeffs *c, const double *F0, const double *dF0,
+                        const mct_td_options *o) {
+    MCT_REQUIRE(out && h && c && F0 && dF0 && o, MCT_BAD_ARGUMENT, "NULL argument to mct_equation_create");
+    *out = nullptr;
+    MCT_REQUIRE(h->type == K_SC3D || h->type == K_TAGGED3D, MCT_UNSUPPORTED, "kernel type not implemented on the device yet");
+    MCT_REQUIRE(o->N >= 2 && o->dt > 0 && o->t_max > 0 && o->tolerance >= 0 && o->max_iterations >= 1, MCT_BAD_ARGUMENT,
+                "bad solver options");
+    MCT_REQUIRE(o->init_with_memory == 1, MCT_UNSUPPORTED, "init_with_memory=false is not supported on the device");
+    MCT_CUDA(cudaSetDevice(h->device));
+    const int Nk = h->Nk;
+    mct_equation_t q = new mct_equation_s();
+    q->kernel = h; q->Nk = Nk; q->opts = *o; q->nblocks = count_blocks(o);
+    q->nt = 1 + 2L * o->N + 2L * o->N * q->nblocks;
+    if (h->type == K_TAGGED3D && h->nt < q->nt) {
+        delete q;
+        set_error("collective trajectory is shorter than this solve (tDict KeyError in the reference)");
+        return MCT_BAD_ARGUMENT;
+    }
+    std::vector<double> host(6 * (size_t)Nk);
+    int rc = expand_coef(c->alpha_kind, c->alpha_scalar, c->alpha, Nk, host.data(), "alpha");
+    if (!rc) rc = expand_coef(c->beta_kind, c->beta_scalar, c->beta, Nk, host.data() + Nk, "beta");
+    if (!rc) rc = expand_coef(c->gamma_kind, c->gamma_scalar, c->gamma, Nk, host.data() + 2 * Nk, "gamma");
+    if (rc) { delete q; return rc; }
+    if (c->delta) memcpy(host.data() + 3 * Nk, c->delta, Nk * sizeof(double));
+    else std::fill(host.begin() + 3 * Nk, host.begin() + 4 * Nk, 0.0);
+    memcpy(host.data() + 4 * Nk, F0, Nk * sizeof(double));
+    memcpy(host.data() + 5 * Nk, dF0, Nk * sizeof(double));
+    q->second_order = 0;
+    for (int i = 0; i < Nk; i++) if (host[i] != 0.0) q->second_order = 1;   // !iszero(alpha)  src/EulerSolver.jl:55
+    if (q->second_order) {
+        for (int i = 0; i < Nk; i++)
+            if (host[i] == 0.0) { delete q; set_error("alpha has zero and non-zero entries (singular)"); return MCT_BAD_ARGUMENT; }
+    } else {
+        for (int i = 0; i < Nk; i++)
+            if (host[Nk + i] == 0.0) { delete q; set_error("alpha = 0 needs beta != 0"); return MCT_BAD_ARGUMENT; }
+    }
+    const size_t ring = (size_t)4 * Nk * 4 * o->N, traj = (size_t)q->nt * Nk;
+    cudaError_t e = cudaMalloc(&q->d_coef, host.size() * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&q->d_ring, ring * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&q->d_F, 2 * traj * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&q->d_status, 64);
+    if (e == cudaSuccess) {
+        q->d_K = q->d_F + traj;
+        q->d_evals = (long long *)((char *)q->d_status + 16);
+        e = cudaMemcpy(q->d_coef, host.data(), host.size() * sizeof(double), cudaMemcpyHostToDevice);
+    }
+    if (e == cudaSuccess) e = cudaMemset(q->d_ring, 0, ring * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemset(q->d_status, 0, 64);
+    if (e != cudaSuccess) { mct_equation_destroy(q); return cuda_fail(e, "mct_equation_create", __FILE__, __LINE__); }
+    *out = q;
+    return MCT_OK;
+}
+
+int mct_equation_destroy(mct_equation_t q) {
+    if (!q) return MCT_OK;
+    if (q->kernel) cudaSetDevice(q->kernel->device);
+    cudaFree(q->d_coef); cudaFree(q->d_ring); cudaFree(q->d_F); cudaFree(q->d_status);
+    delete q;
+    return MCT_OK;
+}
+
+int mct_equation_solve_batch(int n, mct_equation_t *eqs, int *status, long *kernel_evals, float *device_ms) {
+    MCT_REQUIRE(n >= 1 && eqs, MCT_BAD_ARGUMENT, "empty batch");
+    for (int i = 0; i < n; i++) MCT_REQUIRE(eqs[i] && eqs[i]->mode == 0, MCT_BAD_ARGUMENT, "bad equation handle");
+    std::vector<long long> ev(n, 0);
+    int rc = run_batch(n, eqs, 0, eqs[0]->opts.tolerance, eqs[0]->opts.max_iterations, status, ev.data(), device_ms);
+    if (kernel_evals) for (int i = 0; i < n; i++) kernel_evals[i] = (long)ev[i];
+    return rc;
+}
+
+int mct_equation_solve(mct_equation_t q, long *kernel_evals, float *device_ms) {
+    int st = 0;
+    long ev = 0;
+    int rc = mct_equation_solve_batch(1, &q, &st, &ev, device_ms);
+    if (kernel_evals) *kernel_evals = ev;
+    return rc;
+}
+
+int mct_equation_download(mct_equation_t q, double *t_out, double *F_out, double *K_out) {
+    MCT_REQUIRE(q, MCT_BAD_ARGUMENT, "NULL equation");
+    MCT_CUDA(cudaSetDevice(q->kernel->device));
+    const size_t traj = (size_t)q->nt * q->Nk;
+    if (F_out) MCT_CUDA(cudaMemcpy(F_out, q->d_F, traj * sizeof(double), cudaMemcpyDeviceToHost));
+    if (K_out) MCT_CUDA(cudaMemcpy(K_out, q->d_K, traj * sizeof(double), cudaMemcpyDeviceToHost));
+    if (t_out) {
+        // t = dt/(4N) * it, exactly as allocate_results! forms it (src/TimeDoublingSolver.jl:431-434)
+        const int N = q->opts.N;
+        long p = 0;
+        t_out[p++] = 0.0;
+        double Dt = q->opts.dt;
+        const double d0 = Dt / (4.0 * N);
+        for (int it = 1; it <= 2 * N; it++) t_out[p++] = d0 * it;
+        for (int b = 0; b < q->nblocks; b++, Dt *= 2.0) {
+            const double dl = Dt / (4.0 * N);
+            for (int it = 2 * N + 1; it <= 4 * N; it++) t_out[p++] = dl * it;
+        }
+    }
+    return MCT_OK;
+}
+
+int mct_td_solve(mct_kernel_t h, const mct_coeffs *c, const double *F0, const double *dF0, const mct_td_options *o,
+                 double *t_out, double *F_out, double *K_out, long *kernel_evals) {
+    mct_equation_t q = nullptr;
+    int rc = mct_equation_create(&q, h, c, F0, dF0, o);
+    if (rc) return rc;
+    rc = mct_equation_solve(q, kernel_evals, nullptr);
+    int rc2 = mct_equation_download(q, t_out, F_out, K_out);
+    mct_equation_destroy(q);
+    return rc ? rc : rc2;
+}
+
+int mct_steady_state(mct_kernel_t h, const double *gamma, const double *F0, double tolerance, long max_iterations,
+                     double *F_out, double *K_out, long *iterations) {
+    MCT_REQUIRE(h && gamma && F0 && F_out && K_out, MCT_BAD_ARGUMENT, "NULL argument to mct_steady_state");
+    MCT_REQUIRE(h->type == K_SC3D, MCT_UNSUPPORTED, "steady state is implemented for the collective single-component kernel");
+    MCT_CUDA(cudaSetDevice(h->device));
+    const int Nk = h->Nk;
+    mct_equation_s q;
+    q.kernel = h; q.Nk = Nk; q.mode = 1; q.nt = 1;
+    q.opts.N = 2; q.opts.dt = 1.0; q.nblocks = 0;
+    std::vector<double> host(6 * (size_t)Nk, 0.0);
+    memcpy(host.data() + 2 * Nk, gamma, Nk * sizeof(double));
+    memcpy(host.data() + 4 * Nk, F0, Nk * sizeof(double));
+    MCT_CUDA(cudaMalloc(&q.d_coef, (host.size() + 2 * Nk) * sizeof(double)));
+    q.d_F = q.d_coef + host.size(); q.d_K = q.d_F + Nk;
+    cudaError_t e = cudaMalloc(&q.d_status, 64);
+    if (e == cudaSuccess) e = cudaMemset(q.d_status, 0, 64);
+    if (e == cudaSuccess) e = cudaMemcpy(q.d_coef, host.data(), host.size() * sizeof(double), cudaMemcpyHostToDevice);
+    q.d_evals = (long long *)((char *)q.d_status + 16);
+    int rc = MCT_OK;
+    long long it = 0;
+    int st = 0;
+    if (e != cudaSuccess) rc = cuda_fail(e, "mct_steady_state", __FILE__, __LINE__);
+    if (!rc) {
+        mct_equation_t qp = &q;
+        rc = run_batch(1, &qp, 1, tolerance, max_iterations, &st, &it, nullptr);
+    }
+    if (rc == MCT_OK || rc == MCT_NOT_CONVERGED) {
+        cudaMemcpy(F_out, q.d_F, Nk * sizeof(double), cudaMemcpyDeviceToHost);
+        cudaMemcpy(K_out, q.d_K, Nk * sizeof(double), cudaMemcpyDeviceToHost);
+    }
+    if (iterations) *iterations = (long)it;
+    if (rc == MCT_NOT_CONVERGED) set_error("The recursive iteration did not converge.");
+    cudaFree(q.d_coef); cudaFree(q.d_status);
+    return rc;
+}
+
+}  // extern "C"

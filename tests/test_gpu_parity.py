@@ -1,0 +1,198 @@
+"""Parity of the CUDA path (through the C ABI of libmct_sm100a.so) against the CPU oracle and the reference goldens.
+
+Tolerances (BASELINE.json north_star): max|dF(k,t)| <= 1e-10 away from the critical point for the same solver
+settings; relative <= 1e-6 for tau_alpha and f(k) near eta_c.  Kernel evaluations differ from the reference only by
+summation order (the reference's own sequential recursion carries ~2e-12 relative error), so
+single evaluations are compared at rtol 1e-11.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import oracle as O
+import problems as P
+from conftest import load_pkg
+
+pytestmark = pytest.mark.gpu
+pkg = load_pkg()
+
+KERNEL_RTOL = 1e-11
+
+
+def gpu_kernel(p, **kw):
+    return pkg.ModeCouplingKernel(p["rho"], p["kBT"], p["m"], p["k"], p["Sk"], **kw)
+
+
+def gpu_solve(p, e, kernel=None, **solver_kw):
+    kern = kernel or gpu_kernel(p)
+    eq = pkg.MemoryEquation(e["alpha"], e["beta"], e["gamma"], e["delta"], e["F0"], e["dF0"], kern)
+    solver = pkg.TimeDoublingSolver(**solver_kw)
+    return pkg.solve(eq, solver), solver
+
+
+def oracle_solve(p, e, kernel=None, **kw):
+    kern = kernel or O.sc3d(p["rho"], 1.0, 1.0, p["k"], p["Sk"])
+    return O.td_solve(kern, e["alpha"], e["beta"], e["gamma"], e["delta"], e["F0"], e["dF0"], **kw)
+
+
+# ------------------------------------------------------------------------------------------ kernel evaluation
+@pytest.mark.parametrize("Nk", [2, 3, 20, 100, 257, 500, 1000])
+def test_eval_random_F_matches_oracle(Nk):
+    p = P.hard_spheres(Nk, 0.51)
+    F = np.random.default_rng(0).random(Nk)
+    ref = O.sc3d(p["rho"], 1.0, 1.0, p["k"], p["Sk"]).evaluate(F)
+    got = pkg.evaluate_kernel(gpu_kernel(p), F, 0.0)
+    assert np.max(np.abs(got - ref) / np.abs(ref)) < KERNEL_RTOL
+
+
+def test_eval_from_host_tables_equals_device_built_tables():
+    p = P.hard_spheres(200, 0.50)
+    V = pkg.vertex_tables(p["rho"], 1.0, 1.0, p["k"], p["Sk"])
+    F = p["Sk"]
+    a = pkg.evaluate_kernel(gpu_kernel(p, tables=V), F)
+    b = pkg.evaluate_kernel(gpu_kernel(p), F)
+    assert np.array_equal(a, b)     # same tables bit for bit => same sums
+
+
+def test_eval_many_and_linearity():
+    """K is a quadratic form in F: K(sF) = s^2 K(F) exactly for s a power of two (size-independent property)."""
+    p = P.hard_spheres(1000, 0.515)
+    kern = gpu_kernel(p)
+    F = np.random.default_rng(1).random((3, 1000))
+    F[1] = 2.0 * F[0]
+    out, _ = pkg.evaluate_kernel_many(kern, F)
+    assert np.array_equal(out[1], 4.0 * out[0])
+    ref = O.sc3d(p["rho"], 1.0, 1.0, p["k"], p["Sk"]).evaluate(F[2])
+    assert np.max(np.abs(out[2] - ref) / np.abs(ref)) < KERNEL_RTOL
+
+
+def test_eval_nonsymmetric_tables_tagged():
+    p = P.hard_spheres(150, 0.50)
+    rng = np.random.default_rng(2)
+    Fc = rng.random((4, 150)); Fs = rng.random(150)
+    ref = O.tagged3d(p["rho"], 1.0, 1.0, p["k"], p["Sk"], Fc).evaluate(Fs, 2)
+
+    class Sol: F = Fc
+    kern = pkg.TaggedModeCouplingKernel(p["rho"], 1.0, 1.0, p["k"], p["Sk"], Sol)
+    got = pkg.evaluate_kernel(kern, Fs, 2)
+    assert np.max(np.abs(got - ref) / np.abs(ref)) < KERNEL_RTOL
+    with pytest.raises(AssertionError):
+        pkg.evaluate_kernel(kern, Fs, 4)        # time not in the collective solution: tDict KeyError in the reference
+
+
+def test_bad_grid_is_rejected():
+    p = P.hard_spheres(32, 0.5)
+    k = p["k"].copy(); k[5] *= 1.001
+    with pytest.raises(AssertionError):
+        pkg.ModeCouplingKernel(p["rho"], 1.0, 1.0, k, p["Sk"])       # @assert all(diff(k_array) .≈ Δk)
+    with pytest.raises(AssertionError):
+        pkg.ModeCouplingKernel(p["rho"], 1.0, 1.0, p["k"] + 0.1, p["Sk"])   # @assert k_array[1] ≈ Δk/2
+
+
+# ------------------------------------------------------------------------------------------ time-doubling solve
+def test_golden_test_MCT_56_and_oracle():
+    p = P.hard_spheres(100, 0.52, rho_roundtrip=True)
+    e = P.overdamped(p)
+    kw = dict(N=2, dt=1e-10, t_max=1e10, tolerance=1e-8, max_iterations=10 ** 8)
+    sol, solver = gpu_solve(p, e, **kw)
+    assert sol.F.sum() == pytest.approx(13740.912031583604, rel=1.5e-8)          # test/test_MCT.jl:56
+    ref = oracle_solve(p, e, **kw)
+    assert np.array_equal(sol.t, ref["t"])
+    assert sol.F.shape == ref["F"].shape
+    # tolerance 1e-8 => iterates may stop one iteration apart; the bound is a few times the solver tolerance
+    assert np.max(np.abs(sol.F - ref["F"])) < 5e-8
+    assert abs(solver.kernel_evals - ref["kernel_evals"]) <= 0.01 * ref["kernel_evals"]
+
+
+@pytest.mark.parametrize("team", [0, 1, 3, 16, 148])
+def test_config2_Nk100_eta051_defaults_vs_oracle(team, monkeypatch):
+    """BASELINE config 2 with the default solver (N=32, tol 1e-10) for several team sizes (CTAs per equation)."""
+    if team:
+        monkeypatch.setenv("MCT_TEAM_SIZE", str(team))
+    p = P.hard_spheres(100, 0.51)
+    e = P.overdamped(p)
+    sol, solver = gpu_solve(p, e)
+    ref = oracle_solve(p, e)
+    assert np.array_equal(sol.t, ref["t"])
+    dF = np.max(np.abs(sol.F - ref["F"]))
+    dK = np.max(np.abs(sol.K - ref["K"]) / (np.abs(ref["K"]) + 1e-300))
+    print(f"team={team} evals gpu={solver.kernel_evals} oracle={ref['kernel_evals']} max|dF|={dF:.2e} max rel dK={dK:.2e}")
+    assert dF <= 1e-10
+    assert abs(solver.kernel_evals - ref["kernel_evals"]) <= 0.01 * ref["kernel_evals"]
+
+
+def test_tight_tolerance_separates_solver_noise_from_kernel_noise():
+    p = P.hard_spheres(100, 0.51)
+    e = P.overdamped(p)
+    kw = dict(N=16, dt=1e-8, t_max=1e4, tolerance=1e-13, max_iterations=10 ** 6)
+    sol, _ = gpu_solve(p, e, **kw)
+    ref = oracle_solve(p, e, **kw)
+    assert np.max(np.abs(sol.F - ref["F"])) <= 2e-12
+
+
+def test_newtonian_golden_test_tagged_59_and_tagged_chain():
+    p = P.hard_spheres(100, 0.514)
+    kw = dict(N=8, dt=1e-5, t_max=1e5, tolerance=1e-8)
+    e = P.newtonian(p)
+    sol, _ = gpu_solve(p, e, **kw)
+    assert sol.F.sum() == pytest.approx(25492.648222645254, rel=1.5e-8)          # test/test_tagged.jl:59
+    ref = oracle_solve(p, e, **kw)
+    assert np.max(np.abs(sol.F - ref["F"])) < 5e-8
+    # tagged particle chained on the device-resident collective trajectory (test/test_tagged.jl:44-55)
+    et = P.tagged_newtonian(p)
+    tk = pkg.TaggedModeCouplingKernel(p["rho"], 1.0, 1.0, p["k"], p["Sk"], sol)
+    sols, _ = gpu_solve(p, et, kernel=tk, **kw)
+    otk = O.tagged3d(p["rho"], 1.0, 1.0, p["k"], p["Sk"], ref["F"])
+    refs = oracle_solve(p, et, kernel=otk, **kw)
+    assert np.max(np.abs(sols.F - refs["F"])) < 5e-8
+    # same through host tables + host trajectory (the path the Julia glue uses)
+    V = pkg.vertex_tables(p["rho"], 1.0, 1.0, p["k"], p["Sk"], tagged=True)
+    sol.F_host_only = True
+    class HostSol: F = sol.F
+    tk2 = pkg.TaggedModeCouplingKernel(p["rho"], 1.0, 1.0, p["k"], p["Sk"], HostSol, tables=V)
+    sols2, _ = gpu_solve(p, et, kernel=tk2, **kw)
+    assert np.max(np.abs(sols2.F - sols.F)) < 1e-12
+    # MSD from the two device solutions, integrated by the oracle's scalar solver (test/test_tagged.jl:62-71)
+    Kmsd = O.msd3d_table(p["rho"], 1.0, 1.0, p["k"], p["Sk"], sol.F, sols.F)
+    msd = O.td_solve(O.tabulated(Kmsd), 1.0, 0.0, 0.0, -6.0, [0.0], [0.0], scalar_mode=True, **kw)
+    assert msd["F"].sum() == pytest.approx(51.75329405084479, rel=1.5e-8)
+
+
+def test_not_converged_raises_domain_error():
+    p = P.hard_spheres(64, 0.52)
+    e = P.overdamped(p)
+    with pytest.raises(pkg.DomainError):
+        gpu_solve(p, e, N=4, dt=1e-6, t_max=1e6, tolerance=1e-14, max_iterations=2)
+
+
+def test_batch_equals_individual_solves():
+    etas = [0.40, 0.45, 0.50, 0.51, 0.515]
+    kw = dict(N=8, dt=1e-8, t_max=1e6, tolerance=1e-10)
+    eqs, singles = [], []
+    for eta in etas:
+        p = P.hard_spheres(96, eta)
+        e = P.overdamped(p)
+        kern = gpu_kernel(p)
+        eqs.append(pkg.MemoryEquation(e["alpha"], e["beta"], e["gamma"], e["delta"], e["F0"], e["dF0"], kern))
+        singles.append(gpu_solve(p, e, kernel=kern, **kw)[0])
+    sols, status, evals, ms = pkg.solve_batch(eqs, pkg.TimeDoublingSolver(**kw))
+    assert status == [0] * len(etas)
+    for a, b in zip(sols, singles):
+        assert np.array_equal(a.F, b.F) and np.array_equal(a.K, b.K)     # same geometry => bitwise identical
+
+
+# ------------------------------------------------------------------------------------------ steady state
+def test_steady_state_golden_test_steady_state_64():
+    p = P.hard_spheres(100, 0.51595, rho_roundtrip=True)
+    sol = pkg.solve_steady_state(p["k"] ** 2 / p["Sk"], p["Sk"], gpu_kernel(p), tolerance=1e-8)
+    assert sol.F.sum() == pytest.approx(19.285439116785284, rel=1.5e-8)          # test/test_steady_state.jl:64
+    ref = O.steady_state(O.sc3d(p["rho"], 1.0, 1.0, p["k"], p["Sk"]), p["k"] ** 2 / p["Sk"], p["Sk"], tolerance=1e-8)
+    assert np.max(np.abs(sol.F[0] - ref["F"]) / np.maximum(np.abs(ref["F"]), 1e-3)) < 1e-6
+    assert abs(sol.iterations - ref["iterations"]) <= 2
+
+
+def test_steady_state_below_critical_point_is_zero():
+    p = P.hard_spheres(100, 0.50)
+    sol = pkg.solve_steady_state(p["k"] ** 2 / p["Sk"], p["Sk"], gpu_kernel(p), tolerance=1e-10)
+    assert sol.F.sum() < 1e-7

@@ -1,0 +1,144 @@
+"""Pins the CPU oracle (oracle/mct_oracle.c) on the reference's own regression goldens.
+Tolerance: the reference's `≈` (rtol = sqrt(eps) ~ 1.5e-8).  Runs on the CPU."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle as O
+import problems as P
+
+RTOL = 1.5e-8
+
+
+def test_sc_time_doubling_golden_test_MCT_56():
+    p = P.hard_spheres(100, 0.52, rho_roundtrip=True)
+    e = P.overdamped(p)
+    kern = O.sc3d(p["rho"], 1.0, 1.0, p["k"], p["Sk"])
+    sol = O.td_solve(kern, e["alpha"], e["beta"], e["gamma"], 0.0, e["F0"], e["dF0"], N=2, dt=1e-10, t_max=1e10, tolerance=1e-8,
+                     max_iterations=10 ** 8)
+    assert sol["status"] == 0
+    assert sol["F"].sum() == pytest.approx(13740.912031583604, rel=RTOL)
+
+
+@pytest.fixture(scope="module")
+def tagged_chain():
+    p = P.hard_spheres(100, 0.514)
+    e = P.newtonian(p)
+    kern = O.sc3d(p["rho"], 1.0, 1.0, p["k"], p["Sk"])
+    kw = dict(N=8, dt=1e-5, t_max=1e5, tolerance=1e-8)
+    sol = O.td_solve(kern, 1.0, 0.0, e["gamma"], 0.0, e["F0"], e["dF0"], **kw)
+    et = P.tagged_newtonian(p)
+    tk = O.tagged3d(p["rho"], 1.0, 1.0, p["k"], p["Sk"], sol["F"])
+    sols = O.td_solve(tk, 1.0, 0.0, et["gamma"], 0.0, et["F0"], et["dF0"], **kw)
+    return p, sol, sols, kw
+
+
+def test_collective_golden_test_tagged_59(tagged_chain):
+    _, sol, _, _ = tagged_chain
+    assert sol["F"].sum() == pytest.approx(25492.648222645254, rel=RTOL)
+
+
+def test_msd_chain_golden_test_tagged_71(tagged_chain):
+    p, sol, sols, kw = tagged_chain
+    Kmsd = O.msd3d_table(p["rho"], 1.0, 1.0, p["k"], p["Sk"], sol["F"], sols["F"])
+    msd = O.td_solve(O.tabulated(Kmsd), 1.0, 0.0, 0.0, -6.0, [0.0], [0.0], scalar_mode=True, **kw)
+    assert msd["F"].sum() == pytest.approx(51.75329405084479, rel=RTOL)
+
+
+def test_steady_state_golden_test_steady_state_64():
+    p = P.hard_spheres(100, 0.51595, rho_roundtrip=True)
+    kern = O.sc3d(p["rho"], 1.0, 1.0, p["k"], p["Sk"])
+    ss = O.steady_state(kern, p["k"] ** 2 / p["Sk"], p["Sk"], tolerance=1e-8)
+    assert ss["status"] == 0
+    assert ss["F"].sum() == pytest.approx(19.285439116785284, rel=RTOL)
+
+
+def test_scalar_f2_steady_state_test_steady_state_8():
+    ss = O.steady_state(O.f2(4.00000001), [1.0], [1.0], tolerance=1e-10)
+    assert abs(ss["F"][0] - 0.5) < 1e-3
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/test/Sk_MC2.txt"), reason="reference fixture not on this box")
+def test_mc_steady_state_golden_test_steady_state_104():
+    Nk = 100
+    diam = np.array([0.8, 1.0]); cr = np.array([0.2, 0.8]); cr /= cr.sum()
+    rho = 6 * 0.55 / (np.pi * np.sum(cr * diam ** 3)) * cr
+    x = rho / rho.sum()
+    k = P.sf.wavenumber_grid(Nk)
+    data = np.loadtxt("/root/reference/test/Sk_MC2.txt").reshape(-1)
+    Sk = np.transpose(data.reshape((2, 2, 100), order="F") * np.sqrt(x[:, None, None] * x[None, :, None]), (2, 0, 1)).copy()
+    gam = np.einsum("kab,kbc->kac", np.array([np.diag(k[i] ** 2 * x) for i in range(Nk)]), np.linalg.inv(Sk))
+    ss = O.steady_state(O.mc3d(rho, 1.0, np.ones(2), k, Sk), O._blocks(gam), O._blocks(Sk), tolerance=1e-12)
+    assert ss["F"].sum() == pytest.approx(45.50146332163797, rel=RTOL)
+
+
+@pytest.fixture(scope="module")
+def mixture_chain():
+    b = P.binary_mixture()
+    Nk = b["Nk"]
+    kern = O.mc3d(b["rho"], 1.0, b["m"], b["k"], b["Sk"])
+    kw = dict(N=4, dt=1e-4, t_max=1e3, tolerance=1e-12, max_iterations=20000)
+    sol = O.td_solve(kern, 1.0, 0.0, O._blocks(b["gamma"]), np.zeros(Nk * 4), O._blocks(b["Sk"]), np.zeros(Nk * 4), **kw)
+    return b, kern, sol, kw
+
+
+def test_mc_fast_kernel_equals_brute_force_test_MCMCT_192(mixture_chain):
+    b, kern, _, _ = mixture_chain
+    naive = O.mc3d(b["rho"], 1.0, b["m"], b["k"], b["Sk"], naive=True)
+    F = O._blocks(np.random.default_rng(0).random((b["Nk"], 2, 2)))
+    a, c = kern.evaluate(F), naive.evaluate(F)
+    assert np.allclose(a, c, rtol=RTOL, atol=0)
+
+
+def test_mc_time_doubling_golden_test_MCMCT_211(mixture_chain):
+    b, _, sol, _ = mixture_chain
+    Fend = sol["F"][-1].reshape(b["Nk"], 4)[18].reshape(2, 2, order="F")
+    gold = np.array([[0.13881069002073976, 0.04192527228732725], [0.041925272287327266, 0.52419581715369]])
+    assert np.allclose(Fend, gold, rtol=RTOL, atol=0)
+
+
+def test_mc_tagged_and_msd_goldens_test_MCMCT_212_226(mixture_chain):
+    b, _, sol, kw = mixture_chain
+    Nk = b["Nk"]
+    traj = sol["F"].reshape(-1, Nk, 4)
+    tk = O.tagged_mc3d(1, b["rho"], 1.0, b["m"], b["k"], b["Sk"], traj)
+    ts = O.td_solve(tk, 1.0, 0.0, b["k"] ** 2 / b["m"][1], 0.0, np.ones(Nk), np.zeros(Nk), **kw)
+    assert ts["F"][-1][18] == pytest.approx(0.7678799482793754, rel=RTOL)
+    Kt = O.msd_mc3d_table(1, b["rho"], 1.0, b["m"], b["k"], b["Sk"], traj, ts["F"])
+    ms = O.td_solve(O.tabulated(Kt), 1.0, 0.0, 0.0, -6.0, [0.0], [0.0], scalar_mode=True, **kw)
+    assert ms["F"].sum() == pytest.approx(0.6057207573375025, rel=RTOL)
+
+
+def test_ddim_matches_bengtzelius_test_dDimMCT_consistency_69():
+    p = P.hard_spheres(20, 0.50)
+    kd = O.ddim(p["rho"], 1.0, 1.0, p["k"], p["Sk"], 3)
+    ks = O.sc3d(p["rho"], 1.0, 1.0, p["k"], p["Sk"])
+    assert np.abs(kd.evaluate(p["Sk"]) - ks.evaluate(p["Sk"])).sum() < 1e-8
+
+
+def test_ddim_critical_point_2d_test_dDimMCT_crit_pt_96_97():
+    from scipy.special import j0, j1
+    k = P.sf.wavenumber_grid(100)
+
+    def ck2d(phi):
+        t1 = -5 * (1 - phi) ** 2 * k ** 2 * j0(k / 2) ** 2 / 4
+        t2 = (4 * ((phi - 20) * phi + 7) + 5 * (1 - phi) ** 2 * k ** 2 / 4) * j1(k / 2) ** 2
+        t3 = 2 * (phi - 13) * (1 - phi) * k * j1(k / 2) * j0(k / 2)
+        return np.pi * (t1 + t2 + t3) / (6 * (1 - phi) ** 3 * k ** 2)
+
+    out = {}
+    for phi in (0.69, 0.70):
+        rho = 4 * phi / np.pi
+        ck = ck2d(phi)
+        Sk = 1 + rho * ck / (1 - rho * ck)
+        out[phi] = O.steady_state(O.ddim(rho, 1.0, 1.0, k, Sk, 2), k ** 2 / Sk, Sk, tolerance=1e-8)["F"].sum()
+    assert out[0.70] == pytest.approx(17.987734457716535, rel=RTOL)
+    assert out[0.69] < 1e-7
+
+
+def test_relaxation_time_test_relaxationtime_6_8():
+    t = 10 ** np.linspace(-10, 10, 10000)
+    F = np.exp(-t / 1e5) * 6
+    assert abs(O.relaxation_time(t, F, mode="log") - 1e5) < 0.1
+    assert abs(O.relaxation_time(t, F, mode="lin") - 1e5) < 1.0
