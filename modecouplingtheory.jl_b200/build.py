@@ -29,7 +29,8 @@ def build(force=False, verbose=False):
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-shared", "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    extra = ["-DMCT_PROFILE"] if os.environ.get("MCT_PROFILE") == "1" else []
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-shared", "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
     subprocess.check_call(cmd)
     return LIB
 

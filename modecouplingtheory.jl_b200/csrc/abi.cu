@@ -200,13 +200,21 @@ static int choose_geometry(mct_kernel_t h, int n_eq, TeamLayout **out, int *ntea
     G = std::min(G, n_sm);
     const int forced = env_int("MCT_TEAM_SIZE", 0);
     if (forced > 0) G = std::min(forced, n_sm);
-    while ((Nk + G - 1) / G > kThreads) G++;   // at most one row per thread in the row-sum phase
+    G = (int)std::max<long long>(1, std::min<long long>(G, total / 64));   // every CTA needs some terms
     nteams = std::max(1, std::min(n_eq, n_sm / G));
 
     // probe geometry (no spill) to learn slot/task counts and the longest slab, then size the resident part
     TeamLayout probe;
     int rc = layout_build_geometry(probe, Nk, G, sym, 1 << 30);
     if (rc) return rc;
+    while (probe.rows_max > kThreads && G < n_sm) {   // one thread per row part
+        layout_free(probe);
+        G = std::min(n_sm, G * 2);
+        rc = layout_build_geometry(probe, Nk, G, sym, 1 << 30);
+        if (rc) return rc;
+    }
+    MCT_REQUIRE(probe.rows_max <= kThreads, MCT_UNSUPPORTED, "Nk too large for this device");
+    nteams = std::max(1, std::min(n_eq, n_sm / G));
     long long max_len = 0;
     for (int c = 0; c < G; c++) max_len = std::max(max_len, probe.cta_off[c + 1] - probe.cta_off[c]);
     const int slots_b = probe.slots_max + kWarps + 2, tasks_b = probe.tasks_max + 2;
@@ -305,25 +313,28 @@ static int run_batch(int n, mct_equation_t *eqs, int mode, double tol, long long
     P.second_order = eqs[0]->second_order;
     P.dt0 = eqs[0]->opts.dt; P.tol = tol; P.max_iter = max_iter;
     P.total_terms = L->total_terms; P.cta_off = L->d_cta_off; P.tasks = L->d_tasks; P.task_begin = L->d_task_begin;
-    P.rows = L->d_rows; P.row_slot = L->d_row_slot;
+    P.rows = L->d_rows; P.row_slot = L->d_row_slot; P.kslot = L->d_kslot; P.xbuf_words = L->xbuf_words;
     P.rows_max = L->rows_max; P.slots_max = L->slots_max; P.tasks_max = std::max(1, L->tasks_max); P.smem_terms = L->smem_terms;
-    P.xstride = 3 * ((P.Nk + 1) & ~1) + 16;
+    P.xstride = 4LL * L->xbuf_words;
     P.spin_limit_cycles = (long long)env_int("MCT_SPIN_LIMIT_MS", 2000) * 2000000LL;
 
-    // communication scratch: exchange buffers, barrier flags, queue, abort flag, equation table
-    const size_t xbytes = (size_t)nteams * 2 * P.xstride * sizeof(double);
-    const size_t fbytes = (size_t)nteams * P.G * kFlagStride * sizeof(unsigned long long);
+    // communication scratch: exchange buffers (all slots armed with the sentinel = 0xFF bytes), queue, abort flag,
+    // equation table
+    const size_t xbytes = (size_t)nteams * P.xstride * sizeof(double);
+    const size_t fbytes = 0;
     const size_t ebytes = (size_t)n * sizeof(EqDev);
     unsigned char *comm = nullptr;
-    const size_t total = xbytes + fbytes + 256 + ebytes;
+    const size_t pbytes = (size_t)P.G * 12 * sizeof(long long);
+    const size_t total = xbytes + fbytes + 256 + ebytes + pbytes;
     MCT_CUDA(cudaMalloc(&comm, total));
     cudaError_t ce = cudaMemsetAsync(comm, 0, total, s);
+    if (ce == cudaSuccess) ce = cudaMemsetAsync(comm, 0xFF, xbytes, s);
     P.xbuf = (double *)comm;
-    P.flags = (unsigned long long *)(comm + xbytes);
     P.queue = (int *)(comm + xbytes + fbytes);
     P.abort_flag = P.queue + 32;
     EqDev *d_eqs = (EqDev *)(comm + xbytes + fbytes + 256);
     P.eqs = d_eqs;
+    P.prof = (long long *)(comm + xbytes + fbytes + 256 + ebytes);
     if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_eqs, eh.data(), ebytes, cudaMemcpyHostToDevice, s);
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (ce == cudaSuccess) ce = cudaEventCreate(&ev0);
@@ -343,6 +354,22 @@ static int run_batch(int n, mct_equation_t *eqs, int mode, double tol, long long
     if (ev1) cudaEventDestroy(ev1);
     if (ce != cudaSuccess) { cudaFree(comm); return cuda_fail(ce, "run_batch", __FILE__, __LINE__); }
     if (rc != MCT_OK) { cudaFree(comm); return rc; }
+#ifdef MCT_PROFILE
+    {
+        std::vector<long long> pr((size_t)P.G * 12);
+        cudaMemcpy(pr.data(), P.prof, pbytes, cudaMemcpyDeviceToHost);
+        static const char *nm[12] = {"P1 stream", "S1 wait", "rowsum+scan+pub", "totals spin", "reduce+K", "Fn+publish F", "F spin",
+                                     "block_max", "step-local", "-", "TOTAL cycles", "TOTAL ns"};
+        const int ctas[3] = {0, P.G / 2, P.G - 1};
+        fprintf(stderr, "[mct profile] Nk=%d G=%d nteams=%d smem_terms=%d; thread 0 of CTA %d / %d / %d (team 0)\n", P.Nk, P.G, nteams,
+                P.smem_terms, ctas[0], ctas[1], ctas[2]);
+        for (int i = 0; i < 12; i++) {
+            fprintf(stderr, "   %-18s", nm[i]);
+            for (int c : ctas) fprintf(stderr, " %13lld (%4.1f%%)", pr[c * 12 + i], 100.0 * pr[c * 12 + i] / (double)pr[c * 12 + 10]);
+            fprintf(stderr, "\n");
+        }
+    }
+#endif
     int worst = MCT_OK;
     for (int i = 0; i < n; i++) {
         int st = 0; long long ev = 0;

@@ -84,73 +84,112 @@ static void row_pieces(int Nk, int ik /*1-based*/, int sym, std::vector<Piece> &
 
 int layout_build_geometry(TeamLayout &L, int Nk, int G, int sym, int smem_terms) {
     L.Nk = Nk; L.G = G; L.sym = sym; L.smem_terms = smem_terms;
-    L.rows_max = (Nk + G - 1) / G;
-    std::vector<std::vector<int>> cta_rows(G);
-    for (int r = 0; r < Nk; r++) {  // snake deal: row cost falls linearly with ik
-        int round = r / G, pos = r % G;
-        int c = (round % 2 == 0) ? pos : G - 1 - pos;
-        cta_rows[c].push_back(r);
+    // All terms in row order form one sequence; CTA c owns the contiguous range [cta_off[c], cta_off[c+1]) of it, so
+    // every CTA streams the same number of terms.  A row cut by a CTA boundary contributes a partial sum to the
+    // earlier CTA's block total; the row itself (its T, K, F, history) belongs to the CTA holding its LAST term.
+    struct RowPiece { Piece p; int row; };
+    std::vector<RowPiece> all;
+    std::vector<long long> row_end(Nk);
+    long long total = 0;
+    for (int r = 0; r < Nk; r++) {
+        std::vector<Piece> ps;
+        row_pieces(Nk, r + 1, sym, ps);
+        for (auto &p : ps) { p.off = total; all.push_back({p, r}); total += p.len; }
+        row_end[r] = total;
     }
-    L.cta_off.assign(G + 1, 0);
+    L.total_terms = (total + 1) / 2 * 2;
     L.pieces.clear();
+    for (auto &rp : all) L.pieces.push_back(rp.p);
+    L.n_pieces = (int)L.pieces.size();
+    L.cta_off.assign(G + 1, 0);
+    for (int c = 1; c < G; c++) L.cta_off[c] = std::min<long long>(total, (total * c / G + 1) / 2 * 2);
+    L.cta_off[G] = total;
+
+    // first pass: rows (row parts) per CTA
+    std::vector<std::vector<int>> cta_rows(G);      // row index of every row part, in order
+    {
+        size_t pi = 0;
+        for (int c = 0; c < G; c++) {
+            const long long lo = L.cta_off[c], hi = L.cta_off[c + 1];
+            while (pi < all.size() && all[pi].p.off + all[pi].p.len <= lo) pi++;
+            for (size_t q = pi; q < all.size() && all[q].p.off < hi; q++)
+                if (cta_rows[c].empty() || cta_rows[c].back() != all[q].row) cta_rows[c].push_back(all[q].row);
+        }
+    }
+    L.rows_max = 1;
+    for (int c = 0; c < G; c++) L.rows_max = std::max(L.rows_max, (int)cta_rows[c].size());
+
     std::vector<Task> tasks;
     std::vector<int> task_begin(G * kWarps + 1, 0);
     std::vector<int> rows(G * L.rows_max, -1), row_slot(G * (L.rows_max + 1), 0);
-    L.slots_max = 0; L.tasks_max = 0;
-    long long goff = 0;
+    L.slots_max = 1; L.tasks_max = 1;
+    size_t pi = 0;
     for (int c = 0; c < G; c++) {
-        L.cta_off[c] = goff;
-        // pieces of this CTA, with local offsets
-        struct LP { Piece p; int row; int loff; };
-        std::vector<LP> lps;
-        int loff = 0;
-        for (size_t lr = 0; lr < cta_rows[c].size(); lr++) {
-            std::vector<Piece> ps;
-            row_pieces(Nk, cta_rows[c][lr] + 1, sym, ps);
-            rows[c * L.rows_max + lr] = cta_rows[c][lr];
-            for (auto &p : ps) {
-                p.off = goff + loff;
-                lps.push_back({p, (int)lr, loff});
-                L.pieces.push_back(p);
-                loff += p.len;
-            }
-        }
-        int Lc = loff;
+        const long long lo = L.cta_off[c], hi = L.cta_off[c + 1];
+        const int Lc = (int)(hi - lo);
         int chunk = (((Lc + kWarps - 1) / kWarps) + 31) / 32 * 32;
         if (chunk == 0) chunk = 32;
-        // tasks = pieces cut at warp-range boundaries and at the shared-memory capacity boundary
-        int slot = 0;
-        int cur_row = -1;
+        for (size_t lr = 0; lr < cta_rows[c].size(); lr++) {
+            const int r = cta_rows[c][lr];
+            // owned (its last term is here): store ik; partial row whose tail lives in a later CTA: store -(ik+2)
+            rows[c * L.rows_max + lr] = (row_end[r] <= hi) ? r : -(r + 2);
+        }
+        int slot = -1, cur_lr = -1, last_row = -1, last_warp = -1;
         std::vector<std::vector<Task>> per_warp(kWarps);
-        for (auto &lp : lps) {
-            while (cur_row < lp.row) { cur_row++; row_slot[c * (L.rows_max + 1) + cur_row] = slot; }
-            int pos = 0;
-            while (pos < lp.p.len) {
-                int t0 = lp.loff + pos;
-                int w = std::min(t0 / chunk, kWarps - 1);
-                int wend = (w == kWarps - 1) ? Lc : (w + 1) * chunk;
-                int n = std::min(lp.p.len - pos, wend - t0);
-                int where = (t0 >= smem_terms) ? 1 : 0;
+        while (pi < all.size() && all[pi].p.off + all[pi].p.len <= lo) pi++;
+        for (size_t q = pi; q < all.size() && all[q].p.off < hi; q++) {
+            const Piece &pc = all[q].p;
+            const int row = all[q].row;
+            // part of the piece inside this CTA
+            int pos = (int)std::max<long long>(0, lo - pc.off);
+            const int pend = (int)std::min<long long>(pc.len, hi - pc.off);
+            while (pos < pend) {
+                const int t0 = (int)(pc.off + pos - lo);       // offset inside the CTA slab
+                const int w = std::min(t0 / chunk, kWarps - 1);
+                const int wend = (w == kWarps - 1) ? Lc : (w + 1) * chunk;
+                int n = std::min(pend - pos, wend - t0);
+                const int where = (t0 >= smem_terms) ? 1 : 0;
                 if (!where && t0 + n > smem_terms) n = smem_terms - t0;
-                Task t{lp.p.a0 + pos, lp.p.b0 + lp.p.bdir * pos, lp.p.bdir, n, t0, slot++, where, 0};
+                if (row != last_row || w != last_warp) {        // new (warp,row) group -> new partial-sum slot
+                    if (last_warp >= 0) per_warp[last_warp].back().flush = 1;
+                    slot++;
+                    last_warp = w;
+                }
+                if (row != last_row) { cur_lr++; row_slot[c * (L.rows_max + 1) + cur_lr] = slot; last_row = row; }
+                Task t{pc.a0 + pos, pc.b0 + pc.bdir * pos, pc.bdir, n, t0, slot, where, 0};
                 per_warp[w].push_back(t);
                 pos += n;
             }
         }
-        for (int r = cur_row + 1; r <= L.rows_max; r++) row_slot[c * (L.rows_max + 1) + r] = slot;
+        if (last_warp >= 0) per_warp[last_warp].back().flush = 1;
+        slot++;   // number of slots
+        for (int r = cur_lr + 1; r <= L.rows_max; r++) row_slot[c * (L.rows_max + 1) + r] = slot;
         L.slots_max = std::max(L.slots_max, slot);
         for (int w = 0; w < kWarps; w++) {
             task_begin[c * kWarps + w] = (int)tasks.size();
             L.tasks_max = std::max(L.tasks_max, (int)per_warp[w].size());
             tasks.insert(tasks.end(), per_warp[w].begin(), per_warp[w].end());
         }
-        goff += (Lc + 1) / 2 * 2;  // keep every slab 16-byte aligned
     }
     task_begin[G * kWarps] = (int)tasks.size();
-    L.cta_off[G] = goff;
-    L.total_terms = goff;
-    L.n_pieces = (int)L.pieces.size();
 
+    // Exchange buffer geometry (see td_sc.cu): every 128-byte line has exactly ONE writer CTA.  Line c (c < G)
+    // carries the three block totals of CTA c (+ one spare word); after these G lines, CTA c owns LF lines holding
+    // the per-wavenumber values of the rows it owns, in row order.
+    {
+        const int LF = (L.rows_max + 15) / 16;
+        std::vector<int> kslot(Nk, 0);
+        for (int c = 0; c < G; c++) {
+            int idx = 0;
+            for (int lr = 0; lr < L.rows_max; lr++) {
+                const int r = rows[c * L.rows_max + lr];
+                if (r >= 0) kslot[r] = 16 * G + 16 * LF * c + idx++;
+            }
+        }
+        L.xbuf_words = 16 * G + 16 * LF * G;
+        MCT_CUDA(cudaMalloc(&L.d_kslot, Nk * sizeof(int)));
+        MCT_CUDA(cudaMemcpy(L.d_kslot, kslot.data(), Nk * sizeof(int), cudaMemcpyHostToDevice));
+    }
     MCT_CUDA(cudaMalloc(&L.d_tasks, std::max<size_t>(1, tasks.size()) * sizeof(Task)));
     MCT_CUDA(cudaMemcpy(L.d_tasks, tasks.data(), tasks.size() * sizeof(Task), cudaMemcpyHostToDevice));
     MCT_CUDA(cudaMalloc(&L.d_task_begin, task_begin.size() * sizeof(int)));
@@ -168,7 +207,7 @@ int layout_build_geometry(TeamLayout &L, int Nk, int G, int sym, int smem_terms)
 
 void layout_free(TeamLayout &L) {
     cudaFree(L.d_tab); cudaFree(L.d_tasks); cudaFree(L.d_task_begin); cudaFree(L.d_rows); cudaFree(L.d_row_slot);
-    cudaFree(L.d_cta_off); cudaFree(L.d_pieces);
+    cudaFree(L.d_cta_off); cudaFree(L.d_pieces); cudaFree(L.d_kslot);
     L = TeamLayout();
 }
 

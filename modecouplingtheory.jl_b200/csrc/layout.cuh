@@ -19,9 +19,9 @@ struct Task {      // a run of consecutive terms of one row, executed by one war
     int bdir;      // F2 index step per term: +1 (diagonals) or -1 (antidiagonals); F1 always steps +1
     int len;       // number of terms
     int off;       // offset of the first term inside the CTA slab
-    int slot;      // partial-sum slot inside the CTA
+    int slot;      // partial-sum slot inside the CTA (shared by consecutive tasks of one row in one warp)
     int where;     // 0: slab part resident in shared memory, 1: part spilled to global (L2)
-    int pad;
+    int flush;     // 1: last task of its slot -> reduce across the warp and store the partial sum
 };
 
 struct Piece {     // a run of terms of one row, used to build the slab from the Nk x Nk tables
@@ -45,6 +45,8 @@ struct TeamLayout {
     int *d_rows = nullptr;        // [G][rows_max]   row index ik (0-based) or -1
     int *d_row_slot = nullptr;    // [G][rows_max+1] slot range of each local row
     long long *d_cta_off = nullptr;  // [G+1]
+    int *d_kslot = nullptr;          // [Nk] word offset of wavenumber k's slot in an exchange buffer
+    int xbuf_words = 0;              // words (doubles) of one exchange buffer
     std::vector<Piece> pieces;    // host copy (kept for building more slabs with the same geometry)
     Piece *d_pieces = nullptr;
     int n_pieces = 0;

@@ -30,15 +30,17 @@ struct SolveParams {
     const int *task_begin;
     const int *rows;
     const int *row_slot;
+    const int *kslot;           // [Nk] exchange-slot word of every wavenumber
+    int xbuf_words;             // words of one exchange buffer
     int rows_max, slots_max, tasks_max, smem_terms;
     // team communication
-    double *xbuf;               // [nteams][2][xstride]
-    int xstride;
-    unsigned long long *flags;  // [nteams][G][kFlagStride]
+    double *xbuf;               // [nteams][xstride]: four rotating exchange buffers of 3*Nk self-validating slots
+    long long xstride;
     int *queue;                 // next equation to solve
     int *abort_flag;
     const EqDev *eqs;
     long long spin_limit_cycles;
+    long long *prof;            // [nteams][10] phase cycle counters (only filled when built with -DMCT_PROFILE)
 };
 
 size_t td_sc_smem_bytes(int Nk, int G, int slots_max, int tasks_max, int rows_max, int smem_terms);

@@ -46,3 +46,26 @@ def binary_mixture(Nk=50, phi=0.55):
     J = np.array([np.diag(k[i] ** 2 * x / m) for i in range(Nk)])
     gamma = np.einsum("kab,kbc->kac", J, Sinv)
     return dict(Nk=Nk, Ns=2, rho=rho, kBT=1.0, m=m, k=k, Sk=Sk, gamma=gamma, x=x)
+
+
+def exact_sc3d_eval(V, k, F1, F2):
+    """Extended-precision (x87 long double) evaluation of the Bengtzelius recursion
+    T_m[ik] = T_m[ik-1] + sum_iq (A[iq,iq+ik-1] + A[iq+ik-1,iq]) - sum_{iq<ik} A[iq,ik-iq]   (docs/src/MCT.md:266-274)
+    with A_m = V_m .* (F1 F2'), K = k T1 + T2/k^3 + T3/k.  Arbiter between two float64 summation orders."""
+    Nk = len(k)
+    ld = np.longdouble
+    Ts = []
+    for Vm in V:
+        A = np.asarray(Vm).astype(ld) * (np.asarray(F1).astype(ld)[:, None] * np.asarray(F2).astype(ld)[None, :])
+        Aflip = A[:, ::-1]
+        T = np.zeros(Nk, dtype=ld)
+        T[0] = np.trace(A)
+        for ik in range(2, Nk + 1):
+            d = ik - 1
+            inc = np.trace(A, offset=d) + np.trace(A, offset=-d)
+            # antidiagonal iq + ip = ik (1-based), i.e. a + b = ik - 2 (0-based): offset in the column-flipped matrix
+            inc -= np.trace(Aflip, offset=(Nk - 1) - (ik - 2))
+            T[ik - 1] = T[ik - 2] + inc
+        Ts.append(T)
+    kl = np.asarray(k).astype(ld)
+    return kl * Ts[0] + Ts[1] / kl ** 3 + Ts[2] / kl

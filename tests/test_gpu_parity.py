@@ -37,13 +37,26 @@ def oracle_solve(p, e, kernel=None, **kw):
 
 
 # ------------------------------------------------------------------------------------------ kernel evaluation
+def _rel(a, b):
+    return float(np.max(np.abs(a - b) / np.abs(b)))
+
+
 @pytest.mark.parametrize("Nk", [2, 3, 20, 100, 257, 500, 1000])
-def test_eval_random_F_matches_oracle(Nk):
+@pytest.mark.parametrize("smooth", [True, False])
+def test_eval_matches_oracle_within_reference_rounding(Nk, smooth):
+    """The CUDA sums and the reference-order recursion are two float64 summation orders of the same numbers.  An
+    extended-precision sum arbitrates: the CUDA result must be accurate to 1e-12, and may differ from the
+    reference order by no more than the reference order's own rounding error (which grows to ~1e-9 at Nk=1000)."""
     p = P.hard_spheres(Nk, 0.51)
-    F = np.random.default_rng(0).random(Nk)
-    ref = O.sc3d(p["rho"], 1.0, 1.0, p["k"], p["Sk"]).evaluate(F)
+    F = p["Sk"] if smooth else np.random.default_rng(0).random(Nk)
+    okern = O.sc3d(p["rho"], 1.0, 1.0, p["k"], p["Sk"])
+    ref = okern.evaluate(F)
+    exact = P.exact_sc3d_eval(okern.tables(), p["k"], F, F)
     got = pkg.evaluate_kernel(gpu_kernel(p), F, 0.0)
-    assert np.max(np.abs(got - ref) / np.abs(ref)) < KERNEL_RTOL
+    err_gpu, err_ref = _rel(got, exact), _rel(ref, exact)
+    print(f"Nk={Nk} smooth={smooth}: |gpu-exact|={err_gpu:.2e} |oracle-exact|={err_ref:.2e} |gpu-oracle|={_rel(got, ref):.2e}")
+    assert err_gpu < 1e-12
+    assert _rel(got, ref) <= 2.0 * err_ref + 1e-12
 
 
 def test_eval_from_host_tables_equals_device_built_tables():
@@ -63,8 +76,9 @@ def test_eval_many_and_linearity():
     F[1] = 2.0 * F[0]
     out, _ = pkg.evaluate_kernel_many(kern, F)
     assert np.array_equal(out[1], 4.0 * out[0])
-    ref = O.sc3d(p["rho"], 1.0, 1.0, p["k"], p["Sk"]).evaluate(F[2])
-    assert np.max(np.abs(out[2] - ref) / np.abs(ref)) < KERNEL_RTOL
+    okern = O.sc3d(p["rho"], 1.0, 1.0, p["k"], p["Sk"])
+    exact = P.exact_sc3d_eval(okern.tables(), p["k"], F[2], F[2])
+    assert _rel(out[2], exact) < 1e-12
 
 
 def test_eval_nonsymmetric_tables_tagged():
