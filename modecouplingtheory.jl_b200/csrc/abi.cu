@@ -25,8 +25,8 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
 
 enum KernelType { K_SC3D = 1, K_TAGGED3D = 2, K_MC3D = 3, K_DDIM = 5 };
 
-// geometry of a team layout is shared by every kernel handle with the same (device, Nk, G, sym, smem_terms)
-using GeomKey = std::tuple<int, int, int, int, int>;
+// geometry of a team layout is shared by every kernel handle with the same (device, Nk, G, sym)
+using GeomKey = std::tuple<int, int, int, int>;
 static std::mutex g_geom_mutex;
 static std::map<GeomKey, TeamLayout *> g_geoms;
 
@@ -169,14 +169,14 @@ static int upload_traj(mct_kernel_t h, long nt, const double *Fc) {
 }
 
 // ---- team geometry selection ------------------------------------------------------------------------------
-static long long total_terms_of(int Nk, int sym) {
-    long long t = 0;
+static long long total_groups_of(int Nk, int sym) {
+    long long g = 0;
     for (int ik = 1; ik <= Nk; ik++) {
-        int d = ik - 1;
-        if (sym) t += (Nk - d) + (ik - 1) / 2 + (ik % 2 == 0 ? 1 : 0);
-        else t += (long long)(Nk - d) * (d > 0 ? 2 : 1) + (ik - 1);
+        const int d = ik - 1;
+        const int t = sym ? (Nk - d) + (ik - 1) / 2 + (ik % 2 == 0 ? 1 : 0) : (Nk - d) * (d > 0 ? 2 : 1) + (ik - 1);
+        g += (t + 31) / 32;
     }
-    return t;
+    return g;
 }
 
 static int env_int(const char *name, int dflt) {
@@ -184,55 +184,64 @@ static int env_int(const char *name, int dflt) {
     return (v && *v) ? atoi(v) : dflt;
 }
 
+struct Residency { int TR, TS, lane_cap; };
+
+// How the T groups of every warp are kept: TR in registers (a kernel instantiation), TS in shared memory, rest in L2.
+static Residency choose_residency(const TeamLayout &L, size_t smem_optin) {
+    Residency r;
+    const int trmax = std::min(td_sc_max_reg_groups(), env_int("MCT_MAX_REG_GROUPS", td_sc_max_reg_groups()));
+    r.TR = 0;
+    for (int tr : {4, 8, 12}) if (tr <= trmax) { r.TR = tr; if (tr >= L.T) break; }
+    r.lane_cap = std::max(1, L.went_max);               // one scratch column set per (warp,row) entry; <= 10 (choose_geometry)
+    SolveParams P{};
+    P.Nk = L.Nk; P.G = L.G; P.rows_max = L.rows_max; P.ent_max = L.ent_max; P.lane_cap = r.lane_cap; P.TS = 0;
+    const int want = std::max(0, L.T - r.TR);
+    const size_t fixed = td_sc_smem_bytes(P);
+    const size_t per_group = (size_t)kWarps * 32 * (3 * 8 + 4);
+    const int cap = fixed + 64 < smem_optin ? (int)((smem_optin - fixed - 64) / per_group) : 0;
+    r.TS = std::min(want, cap);
+    return r;
+}
+
 // Returns the (cached) geometry for n_eq concurrent equations on this kernel's device.
 static int choose_geometry(mct_kernel_t h, int n_eq, TeamLayout **out, int *nteams_out) {
     const int Nk = h->Nk, sym = h->sym;
     const int n_sm = h->n_sm;
-    const long long total = total_terms_of(Nk, sym);
-    const int target_terms = env_int("MCT_TARGET_TERMS", 4096);
-    // capacity of one CTA: ~ (opt-in shared memory - fixed arrays) / 24 bytes per term
-    const size_t fixed_guess = (size_t)(3 + 3) * (Nk + 2) * 8 + 24 * 1024;
-    const long long cap_guess = h->smem_optin > fixed_guess ? (long long)((h->smem_optin - fixed_guess) / 24) : 1024;
-    int G_fit = (int)std::min<long long>(n_sm, std::max<long long>(1, (total + cap_guess - 1) / cap_guess));
-    int G_lat = (int)std::min<long long>(n_sm, std::max<long long>(1, (total + target_terms - 1) / target_terms));
-    int nteams = std::max(1, std::min(n_eq, n_sm / G_fit));
-    int G = std::max(G_fit, std::min(G_lat, n_sm / nteams));
-    G = std::min(G, n_sm);
-    const int forced = env_int("MCT_TEAM_SIZE", 0);
-    if (forced > 0) G = std::min(forced, n_sm);
-    G = (int)std::max<long long>(1, std::min<long long>(G, total / 64));   // every CTA needs some terms
-    nteams = std::max(1, std::min(n_eq, n_sm / G));
-
-    // probe geometry (no spill) to learn slot/task counts and the longest slab, then size the resident part
-    TeamLayout probe;
-    int rc = layout_build_geometry(probe, Nk, G, sym, 1 << 30);
-    if (rc) return rc;
-    while (probe.rows_max > kThreads && G < n_sm) {   // one thread per row part
-        layout_free(probe);
-        G = std::min(n_sm, G * 2);
-        rc = layout_build_geometry(probe, Nk, G, sym, 1 << 30);
-        if (rc) return rc;
+    const long long groups = total_groups_of(Nk, sym);
+    const int g_cap = std::max(1, std::min(n_sm, Nk / 2));               // at least two rows per CTA
+    const int g_min = (Nk + kThreads - 1) / kThreads;                    // one owner thread per row
+    // on-chip capacity of one CTA in groups per warp: registers + what shared memory can hold
+    const int t_chip = td_sc_max_reg_groups() + (int)((h->smem_optin - 48 * 1024 - (size_t)40 * Nk) / ((size_t)kWarps * 32 * 28));
+    int G_fit = (int)std::min<long long>(g_cap, std::max<long long>(g_min, (groups + (long long)kWarps * t_chip - 1) / ((long long)kWarps * t_chip)));
+    int G;
+    if (n_eq == 1) {
+        // latency: as many CTAs as keep every thread busy with a few terms per iteration
+        const int target = env_int("MCT_TARGET_GROUPS", 4);
+        G = (int)std::min<long long>(g_cap, std::max<long long>(G_fit, (groups + (long long)kWarps * target - 1) / ((long long)kWarps * target)));
+    } else {
+        // throughput: the smallest team whose tables stay on chip (the exchange is a per-CTA cost)
+        G = G_fit;
     }
-    MCT_REQUIRE(probe.rows_max <= kThreads, MCT_UNSUPPORTED, "Nk too large for this device");
-    nteams = std::max(1, std::min(n_eq, n_sm / G));
-    long long max_len = 0;
-    for (int c = 0; c < G; c++) max_len = std::max(max_len, probe.cta_off[c + 1] - probe.cta_off[c]);
-    const int slots_b = probe.slots_max + kWarps + 2, tasks_b = probe.tasks_max + 2;
-    const int rows_max = probe.rows_max;
-    layout_free(probe);
-    int cap = td_sc_max_smem_terms(Nk, G, slots_b, tasks_b, rows_max, h->smem_optin);
-    MCT_REQUIRE(cap > 0, MCT_UNSUPPORTED, "shared memory too small for this Nk");
-    const int smem_terms = (int)std::min<long long>(cap, (max_len + 1) / 2 * 2);
+    const int forced = env_int("MCT_TEAM_SIZE", 0);
+    if (forced > 0) G = std::max(g_min, std::min(forced, g_cap));
 
     std::lock_guard<std::mutex> lock(g_geom_mutex);
-    GeomKey key(h->device, Nk, G, sym, smem_terms);
-    auto it = g_geoms.find(key);
-    if (it == g_geoms.end()) {
-        TeamLayout *L = new TeamLayout();
-        rc = layout_build_geometry(*L, Nk, G, sym, smem_terms);
-        if (rc) { delete L; return rc; }
-        it = g_geoms.emplace(key, L).first;
+    std::map<GeomKey, TeamLayout *>::iterator it;
+    while (true) {
+        GeomKey key(h->device, Nk, G, sym);
+        it = g_geoms.find(key);
+        if (it == g_geoms.end()) {
+            TeamLayout *L = new TeamLayout();
+            int rc = layout_build_geometry(*L, Nk, G, sym);
+            if (rc) { delete L; return rc; }
+            it = g_geoms.emplace(key, L).first;
+        }
+        // a warp reduces at most 10 (warp,row) entries per evaluation; short rows in a small team need a larger team
+        if (it->second->went_max <= 10 || G >= g_cap) break;
+        G++;
     }
+    MCT_REQUIRE(it->second->went_max <= 10, MCT_UNSUPPORTED, "internal: no team geometry with <= 10 rows per warp");
+    const int nteams = std::max(1, std::min(n_eq, n_sm / G));
     *out = it->second;
     *nteams_out = nteams;
     return MCT_OK;
@@ -242,8 +251,7 @@ static int ensure_slab(mct_kernel_t h, TeamLayout *L, const double **tab) {
     auto it = h->slabs.find(L);
     if (it != h->slabs.end()) { *tab = it->second; return MCT_OK; }
     double *d = nullptr;
-    MCT_CUDA(cudaMalloc(&d, 3 * (size_t)L->total_terms * sizeof(double)));
-    MCT_CUDA(cudaMemsetAsync(d, 0, 3 * (size_t)L->total_terms * sizeof(double), h->stream));
+    MCT_CUDA(cudaMalloc(&d, 3 * (size_t)L->slab_terms * sizeof(double)));
     int rc;
     if (h->d_V1) rc = layout_fill_from_tables(*L, d, h->d_V1, h->d_V2, h->d_V3, h->stream);
     else rc = layout_fill_from_sk(*L, d, h->d_k, h->d_Ck, h->rho, h->kBT, h->m, h->type == K_TAGGED3D, h->stream);
@@ -309,32 +317,43 @@ static int run_batch(int n, mct_equation_t *eqs, int mode, double tol, long long
         e.status = q->d_status; e.kernel_evals = q->d_evals;
     }
     SolveParams P{};
+    const Residency res = choose_residency(*L, h0->smem_optin);
     P.Nk = h0->Nk; P.G = L->G; P.N = eqs[0]->opts.N; P.nblocks = eqs[0]->nblocks; P.n_eq = n; P.nteams = nteams;
     P.second_order = eqs[0]->second_order;
     P.dt0 = eqs[0]->opts.dt; P.tol = tol; P.max_iter = max_iter;
-    P.total_terms = L->total_terms; P.cta_off = L->d_cta_off; P.tasks = L->d_tasks; P.task_begin = L->d_task_begin;
-    P.rows = L->d_rows; P.row_slot = L->d_row_slot; P.kslot = L->d_kslot; P.xbuf_words = L->xbuf_words;
-    P.rows_max = L->rows_max; P.slots_max = L->slots_max; P.tasks_max = std::max(1, L->tasks_max); P.smem_terms = L->smem_terms;
-    P.xstride = 4LL * L->xbuf_words;
+    P.T = L->T; P.TR = res.TR; P.TS = res.TS; P.lane_cap = res.lane_cap;
+    P.rows_max = L->rows_max; P.ent_max = L->ent_max; P.slab_terms = L->slab_terms;
+    P.desc = L->d_desc; P.cta_meta = L->d_cta_meta; P.ent_begin = L->d_ent_begin; P.warp_ent = L->d_warp_ent; P.row_owner = L->d_row_owner;
+    P.xbuf_words = L->xbuf_words;
+    P.xstride = 4LL * L->xbuf_words + 16;      // four rotating buffers + the arrival counter (own line)
+    P.poll_delay = env_int("MCT_POLL_DELAY", 300);
+    P.poll_backoff = env_int("MCT_POLL_BACKOFF", 100);
+    P.dbg = env_int("MCT_DBG", 0);
     P.spin_limit_cycles = (long long)env_int("MCT_SPIN_LIMIT_MS", 2000) * 2000000LL;
+    if (env_int("MCT_VERBOSE", 0))
+        fprintf(stderr, "[mct] Nk=%d sym=%d n_eq=%d: teams=%d x G=%d, T=%d groups/warp (TR=%d regs, TS=%d smem, %d L2), rows/CTA<=%d, smem=%zu B\n",
+                P.Nk, h0->sym, n, nteams, P.G, P.T, P.TR, P.TS, P.T - std::min(P.T, P.TR) - P.TS, P.rows_max, td_sc_smem_bytes(P));
 
-    // communication scratch: exchange buffers (all slots armed with the sentinel = 0xFF bytes), queue, abort flag,
-    // equation table
+    // communication scratch: exchange buffers and queue mailboxes (all slots armed with the sentinel = 0xFF bytes),
+    // queue, abort flag, equation table
     const size_t xbytes = (size_t)nteams * P.xstride * sizeof(double);
-    const size_t fbytes = 0;
+    const size_t qbytes = (size_t)nteams * 64 * sizeof(double);
     const size_t ebytes = (size_t)n * sizeof(EqDev);
     unsigned char *comm = nullptr;
-    const size_t pbytes = (size_t)P.G * 12 * sizeof(long long);
-    const size_t total = xbytes + fbytes + 256 + ebytes + pbytes;
+    const size_t pbytes = (size_t)P.G * kProfSlots * sizeof(long long);
+    const size_t total = xbytes + qbytes + 256 + ebytes + pbytes;
     MCT_CUDA(cudaMalloc(&comm, total));
     cudaError_t ce = cudaMemsetAsync(comm, 0, total, s);
-    if (ce == cudaSuccess) ce = cudaMemsetAsync(comm, 0xFF, xbytes, s);
+    if (ce == cudaSuccess) ce = cudaMemsetAsync(comm, 0xFF, xbytes + qbytes, s);
+    for (int t = 0; t < nteams && ce == cudaSuccess; t++)      // arrival counters start at zero
+        ce = cudaMemsetAsync(comm + ((size_t)t * P.xstride + 4 * (size_t)P.xbuf_words) * sizeof(double), 0, 16 * sizeof(double), s);
     P.xbuf = (double *)comm;
-    P.queue = (int *)(comm + xbytes + fbytes);
+    P.qbox = (double *)(comm + xbytes);
+    P.queue = (int *)(comm + xbytes + qbytes);
     P.abort_flag = P.queue + 32;
-    EqDev *d_eqs = (EqDev *)(comm + xbytes + fbytes + 256);
+    EqDev *d_eqs = (EqDev *)(comm + xbytes + qbytes + 256);
     P.eqs = d_eqs;
-    P.prof = (long long *)(comm + xbytes + fbytes + 256 + ebytes);
+    P.prof = (long long *)(comm + xbytes + qbytes + 256 + ebytes);
     if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_eqs, eh.data(), ebytes, cudaMemcpyHostToDevice, s);
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (ce == cudaSuccess) ce = cudaEventCreate(&ev0);
@@ -356,17 +375,30 @@ static int run_batch(int n, mct_equation_t *eqs, int mode, double tol, long long
     if (rc != MCT_OK) { cudaFree(comm); return rc; }
 #ifdef MCT_PROFILE
     {
-        std::vector<long long> pr((size_t)P.G * 12);
+        std::vector<long long> pr((size_t)P.G * kProfSlots);
         cudaMemcpy(pr.data(), P.prof, pbytes, cudaMemcpyDeviceToHost);
-        static const char *nm[12] = {"P1 stream", "S1 wait", "rowsum+scan+pub", "totals spin", "reduce+K", "Fn+publish F", "F spin",
-                                     "block_max", "step-local", "-", "TOTAL cycles", "TOTAL ns"};
+        static const char *nm[kProfSlots] = {"stream+warp reduce", "barrier", "row sums+prefix", "F_loc", "publish+delay", "collect", "offset scan+barrier",
+                                            "apply+or-barrier", "between", "step-local", "=exchange alone", "=eval alone", "=eval+exchange", "-", "x:loads", "x:scan", "x:sync", "x:offsets", "x:or-barrier", "-", "-", "-", "-", "-", "-", "-", "-", "-", "-", "-", "TOTAL cycles", "TOTAL ns"};
         const int ctas[3] = {0, P.G / 2, P.G - 1};
-        fprintf(stderr, "[mct profile] Nk=%d G=%d nteams=%d smem_terms=%d; thread 0 of CTA %d / %d / %d (team 0)\n", P.Nk, P.G, nteams,
-                P.smem_terms, ctas[0], ctas[1], ctas[2]);
-        for (int i = 0; i < 12; i++) {
-            fprintf(stderr, "   %-18s", nm[i]);
-            for (int c : ctas) fprintf(stderr, " %13lld (%4.1f%%)", pr[c * 12 + i], 100.0 * pr[c * 12 + i] / (double)pr[c * 12 + 10]);
+        fprintf(stderr, "[mct profile] Nk=%d G=%d nteams=%d T=%d TR=%d TS=%d; thread 0 of CTA %d / %d / %d (team 0)\n", P.Nk, P.G, nteams,
+                P.T, P.TR, P.TS, ctas[0], ctas[1], ctas[2]);
+        for (int i = 0; i < kProfSlots; i++) {
+            if (nm[i][0] == '-') continue;
+            fprintf(stderr, "   %-20s", nm[i]);
+            for (int c : ctas) fprintf(stderr, " %13lld (%4.1f%%)", pr[c * kProfSlots + i], 100.0 * pr[c * kProfSlots + i] / (double)pr[c * kProfSlots + kProfSlots - 2]);
             fprintf(stderr, "\n");
+        }
+        if (getenv("MCT_DUMP_SNAP")) {
+            long long t0 = pr[19];
+            for (int c = 0; c < P.G; c++) t0 = std::min(t0, pr[(size_t)c * kProfSlots + 19]);
+            fprintf(stderr, "snapshot of exchange 1000 (ns after the first publish): cta publish totals_seen barrier1 rows_loaded end\n");
+            for (int c = 0; c < P.G; c++) {
+                fprintf(stderr, "  %3d", c);
+                for (int i = 19; i <= 23; i++) fprintf(stderr, " %6lld", pr[(size_t)c * kProfSlots + i] - t0);
+                fprintf(stderr, "   lanes 2-7:");
+                for (int i = 24; i < 30; i++) fprintf(stderr, " %6lld", pr[(size_t)c * kProfSlots + i] - t0);
+                fprintf(stderr, "\n");
+            }
         }
     }
 #endif

@@ -43,177 +43,187 @@ __global__ void raw_tables_kernel(int Nk, const double *k, const double *Ck, dou
     V1[ix] = v1; V2[ix] = v2; V3[ix] = v3;
 }
 
-__global__ void fill_from_tables_kernel(int Nk, long long total, const Piece *pieces, const double *V1, const double *V2,
-                                        const double *V3, double *tab) {
-    const Piece pc = pieces[blockIdx.x];
-    for (int i = threadIdx.x; i < pc.len; i += blockDim.x) {
-        size_t ix = (size_t)(pc.a0 + i) + (size_t)(pc.b0 + pc.bdir * i) * Nk;
-        tab[pc.off + i] = pc.coef * V1[ix];
-        tab[total + pc.off + i] = pc.coef * V2[ix];
-        tab[2 * total + pc.off + i] = pc.coef * V3[ix];
-    }
+__device__ __forceinline__ double desc_coef(int d) {
+    const int c = (d >> kDescCoefShift) & 3;
+    return c == 0 ? 1.0 : c == 1 ? 2.0 : c == 2 ? -1.0 : -2.0;
 }
 
-__global__ void fill_from_sk_kernel(int Nk, long long total, const Piece *pieces, const double *k, const double *Ck,
-                                    double rho, double D0, double pi2c, double dk, int tagged, double *tab) {
-    const Piece pc = pieces[blockIdx.x];
-    for (int i = threadIdx.x; i < pc.len; i += blockDim.x) {
-        int a = pc.a0 + i, b = pc.b0 + pc.bdir * i;  // A[a,b] = V[a,b] F1[a] F2[b]; q = k[a], p = k[b]
-        double v1, v2, v3;
+// One thread per slab slot: tab_m[slot] = coef * V_m[a,b]  (0 where the slot is padding).
+__global__ void fill_from_tables_kernel(int Nk, long long slab, const int *desc, const double *V1, const double *V2,
+                                        const double *V3, double *tab) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= slab) return;
+    const int d = desc[i];
+    double v1 = 0.0, v2 = 0.0, v3 = 0.0;
+    if (d & kDescValid) {
+        const int a = d & kDescIdxMask, b = (d >> kDescIdxBits) & kDescIdxMask;
+        const size_t ix = (size_t)a + (size_t)b * Nk;
+        const double cf = desc_coef(d);
+        v1 = cf * V1[ix]; v2 = cf * V2[ix]; v3 = cf * V3[ix];
+    }
+    tab[i] = v1; tab[slab + i] = v2; tab[2 * slab + i] = v3;
+}
+
+__global__ void fill_from_sk_kernel(int Nk, long long slab, const int *desc, const double *k, const double *Ck, double rho,
+                                    double D0, double pi2c, double dk, int tagged, double *tab) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= slab) return;
+    const int d = desc[i];
+    double v1 = 0.0, v2 = 0.0, v3 = 0.0;
+    if (d & kDescValid) {
+        const int a = d & kDescIdxMask, b = (d >> kDescIdxBits) & kDescIdxMask;  // A[a,b] = V[a,b] F1[a] F2[b]; q = k[a], p = k[b]
         if (tagged) vertex_tagged(k[b], k[a], Ck[a], D0, rho, pi2c, dk * dk, v1, v2, v3);
         else vertex_collective(k[b], k[a], Ck[b], Ck[a], D0, rho, pi2c, dk, v1, v2, v3);
-        tab[pc.off + i] = pc.coef * v1;
-        tab[total + pc.off + i] = pc.coef * v2;
-        tab[2 * total + pc.off + i] = pc.coef * v3;
+        const double cf = desc_coef(d);
+        v1 = cf * v1; v2 = cf * v2; v3 = cf * v3;
     }
+    tab[i] = v1; tab[slab + i] = v2; tab[2 * slab + i] = v3;
 }
 
-static void row_pieces(int Nk, int ik /*1-based*/, int sym, std::vector<Piece> &out) {
-    int d = ik - 1;
+namespace {
+
+struct Term { int a, b, coef; };   // coef code: 0:+1 1:+2 2:-1 3:-2
+
+// Terms of the increment of row ik (1-based), in a fixed canonical order.
+void row_terms(int Nk, int ik, int sym, std::vector<Term> &out) {
+    out.clear();
+    const int d = ik - 1;
     if (sym) {
-        out.push_back({0, d, +1, Nk - d, 0, d > 0 ? 2.0 : 1.0});
-        int nhalf = (ik - 1) / 2;
-        if (nhalf > 0) out.push_back({0, ik - 2, -1, nhalf, 0, -2.0});
-        if (ik % 2 == 0) out.push_back({ik / 2 - 1, ik / 2 - 1, -1, 1, 0, -1.0});
+        for (int i = 0; i < Nk - d; i++) out.push_back({i, i + d, d > 0 ? 1 : 0});         // A[q,q+d] + A[q+d,q]
+        for (int a = 0; a < (ik - 1) / 2; a++) out.push_back({a, ik - 2 - a, 3});          // -(A[a,b] + A[b,a]), a < b
+        if (ik % 2 == 0) out.push_back({ik / 2 - 1, ik / 2 - 1, 2});                       // -A[a,a]
     } else {
-        out.push_back({0, d, +1, Nk - d, 0, 1.0});
-        if (d > 0) out.push_back({d, 0, +1, Nk - d, 0, 1.0});
-        if (ik >= 2) out.push_back({0, ik - 2, -1, ik - 1, 0, -1.0});
+        for (int i = 0; i < Nk - d; i++) out.push_back({i, i + d, 0});
+        if (d > 0) for (int i = 0; i < Nk - d; i++) out.push_back({i + d, i, 0});
+        for (int a = 0; a <= ik - 2; a++) out.push_back({a, ik - 2 - a, 2});
     }
 }
 
-int layout_build_geometry(TeamLayout &L, int Nk, int G, int sym, int smem_terms) {
-    L.Nk = Nk; L.G = G; L.sym = sym; L.smem_terms = smem_terms;
-    // All terms in row order form one sequence; CTA c owns the contiguous range [cta_off[c], cta_off[c+1]) of it, so
-    // every CTA streams the same number of terms.  A row cut by a CTA boundary contributes a partial sum to the
-    // earlier CTA's block total; the row itself (its T, K, F, history) belongs to the CTA holding its LAST term.
-    struct RowPiece { Piece p; int row; };
-    std::vector<RowPiece> all;
-    std::vector<long long> row_end(Nk);
+int row_nterms(int Nk, int ik, int sym) {
+    const int d = ik - 1;
+    if (sym) return (Nk - d) + (ik - 1) / 2 + (ik % 2 == 0 ? 1 : 0);
+    return (Nk - d) * (d > 0 ? 2 : 1) + (ik - 1);
+}
+
+// Contiguous partition of the rows into G ranges minimising the largest number of groups; every range non-empty.
+void partition_rows(int Nk, int G, int sym, std::vector<int> &row0) {
+    std::vector<int> ng(Nk);
     long long total = 0;
+    int biggest = 0;
+    for (int r = 0; r < Nk; r++) { ng[r] = (row_nterms(Nk, r + 1, sym) + 31) / 32; total += ng[r]; biggest = std::max(biggest, ng[r]); }
+    auto ranges_needed = [&](long long cap) {
+        int n = 1; long long cur = 0;
+        for (int r = 0; r < Nk; r++) { if (cur + ng[r] > cap) { n++; cur = 0; } cur += ng[r]; }
+        return n;
+    };
+    long long lo = std::max<long long>(biggest, (total + G - 1) / G), hi = total;
+    while (lo < hi) { const long long mid = (lo + hi) / 2; if (ranges_needed(mid) <= G) hi = mid; else lo = mid + 1; }
+    row0.assign(G + 1, Nk);
+    int c = 0; long long cur = 0;
+    row0[0] = 0;
     for (int r = 0; r < Nk; r++) {
-        std::vector<Piece> ps;
-        row_pieces(Nk, r + 1, sym, ps);
-        for (auto &p : ps) { p.off = total; all.push_back({p, r}); total += p.len; }
-        row_end[r] = total;
+        const int rows_left = Nk - r, ctas_after = G - 1 - c;      // rows still to place (with r), CTAs after this one
+        if (cur > 0 && (cur + ng[r] > lo || rows_left <= ctas_after)) { c++; row0[c] = r; cur = 0; }
+        cur += ng[r];
     }
-    L.total_terms = (total + 1) / 2 * 2;
-    L.pieces.clear();
-    for (auto &rp : all) L.pieces.push_back(rp.p);
-    L.n_pieces = (int)L.pieces.size();
-    L.cta_off.assign(G + 1, 0);
-    for (int c = 1; c < G; c++) L.cta_off[c] = std::min<long long>(total, (total * c / G + 1) / 2 * 2);
-    L.cta_off[G] = total;
+    for (int i = c + 1; i <= G; i++) row0[i] = Nk;
+}
 
-    // first pass: rows (row parts) per CTA
-    std::vector<std::vector<int>> cta_rows(G);      // row index of every row part, in order
-    {
-        size_t pi = 0;
-        for (int c = 0; c < G; c++) {
-            const long long lo = L.cta_off[c], hi = L.cta_off[c + 1];
-            while (pi < all.size() && all[pi].p.off + all[pi].p.len <= lo) pi++;
-            for (size_t q = pi; q < all.size() && all[q].p.off < hi; q++)
-                if (cta_rows[c].empty() || cta_rows[c].back() != all[q].row) cta_rows[c].push_back(all[q].row);
-        }
-    }
-    L.rows_max = 1;
-    for (int c = 0; c < G; c++) L.rows_max = std::max(L.rows_max, (int)cta_rows[c].size());
+}  // namespace
 
-    std::vector<Task> tasks;
-    std::vector<int> task_begin(G * kWarps + 1, 0);
-    std::vector<int> rows(G * L.rows_max, -1), row_slot(G * (L.rows_max + 1), 0);
-    L.slots_max = 1; L.tasks_max = 1;
-    size_t pi = 0;
+int layout_groups_per_warp(int Nk, int G, int sym, int *rows_max) {
+    std::vector<int> row0;
+    partition_rows(Nk, G, sym, row0);
+    long long gmax = 0; int rmax = 0;
     for (int c = 0; c < G; c++) {
-        const long long lo = L.cta_off[c], hi = L.cta_off[c + 1];
-        const int Lc = (int)(hi - lo);
-        int chunk = (((Lc + kWarps - 1) / kWarps) + 31) / 32 * 32;
-        if (chunk == 0) chunk = 32;
-        for (size_t lr = 0; lr < cta_rows[c].size(); lr++) {
-            const int r = cta_rows[c][lr];
-            // owned (its last term is here): store ik; partial row whose tail lives in a later CTA: store -(ik+2)
-            rows[c * L.rows_max + lr] = (row_end[r] <= hi) ? r : -(r + 2);
-        }
-        int slot = -1, cur_lr = -1, last_row = -1, last_warp = -1;
-        std::vector<std::vector<Task>> per_warp(kWarps);
-        while (pi < all.size() && all[pi].p.off + all[pi].p.len <= lo) pi++;
-        for (size_t q = pi; q < all.size() && all[q].p.off < hi; q++) {
-            const Piece &pc = all[q].p;
-            const int row = all[q].row;
-            // part of the piece inside this CTA
-            int pos = (int)std::max<long long>(0, lo - pc.off);
-            const int pend = (int)std::min<long long>(pc.len, hi - pc.off);
-            while (pos < pend) {
-                const int t0 = (int)(pc.off + pos - lo);       // offset inside the CTA slab
-                const int w = std::min(t0 / chunk, kWarps - 1);
-                const int wend = (w == kWarps - 1) ? Lc : (w + 1) * chunk;
-                int n = std::min(pend - pos, wend - t0);
-                const int where = (t0 >= smem_terms) ? 1 : 0;
-                if (!where && t0 + n > smem_terms) n = smem_terms - t0;
-                if (row != last_row || w != last_warp) {        // new (warp,row) group -> new partial-sum slot
-                    if (last_warp >= 0) per_warp[last_warp].back().flush = 1;
-                    slot++;
-                    last_warp = w;
-                }
-                if (row != last_row) { cur_lr++; row_slot[c * (L.rows_max + 1) + cur_lr] = slot; last_row = row; }
-                Task t{pc.a0 + pos, pc.b0 + pc.bdir * pos, pc.bdir, n, t0, slot, where, 0};
-                per_warp[w].push_back(t);
-                pos += n;
-            }
-        }
-        if (last_warp >= 0) per_warp[last_warp].back().flush = 1;
-        slot++;   // number of slots
-        for (int r = cur_lr + 1; r <= L.rows_max; r++) row_slot[c * (L.rows_max + 1) + r] = slot;
-        L.slots_max = std::max(L.slots_max, slot);
-        for (int w = 0; w < kWarps; w++) {
-            task_begin[c * kWarps + w] = (int)tasks.size();
-            L.tasks_max = std::max(L.tasks_max, (int)per_warp[w].size());
-            tasks.insert(tasks.end(), per_warp[w].begin(), per_warp[w].end());
-        }
+        long long g = 0;
+        for (int r = row0[c]; r < row0[c + 1]; r++) g += (row_nterms(Nk, r + 1, sym) + 31) / 32;
+        gmax = std::max(gmax, g); rmax = std::max(rmax, row0[c + 1] - row0[c]);
     }
-    task_begin[G * kWarps] = (int)tasks.size();
+    if (rows_max) *rows_max = rmax;
+    return (int)((gmax + kWarps - 1) / kWarps);
+}
 
-    // Exchange buffer geometry (see td_sc.cu): every 128-byte line has exactly ONE writer CTA.  Line c (c < G)
-    // carries the three block totals of CTA c (+ one spare word); after these G lines, CTA c owns LF lines holding
-    // the per-wavenumber values of the rows it owns, in row order.
-    {
-        const int LF = (L.rows_max + 15) / 16;
-        std::vector<int> kslot(Nk, 0);
-        for (int c = 0; c < G; c++) {
-            int idx = 0;
-            for (int lr = 0; lr < L.rows_max; lr++) {
-                const int r = rows[c * L.rows_max + lr];
-                if (r >= 0) kslot[r] = 16 * G + 16 * LF * c + idx++;
-            }
+int layout_build_geometry(TeamLayout &L, int Nk, int G, int sym) {
+    MCT_REQUIRE(Nk <= (1 << kDescIdxBits), MCT_UNSUPPORTED, "Nk > 2048 is not supported by the persistent solver");
+    L.Nk = Nk; L.G = G; L.sym = sym;
+    std::vector<int> row0;
+    partition_rows(Nk, G, sym, row0);
+    for (int c = 0; c < G; c++) MCT_REQUIRE(row0[c + 1] > row0[c], MCT_BAD_ARGUMENT, "team larger than the number of rows");
+    int rows_max = 0;
+    L.T = layout_groups_per_warp(Nk, G, sym, &rows_max);
+    L.rows_max = rows_max;
+    const int T = L.T;
+    const long long cta_slots = (long long)kWarps * T * 32;
+    L.slab_terms = cta_slots * G;
+    std::vector<int> desc((size_t)L.slab_terms, 0), meta(4 * G, 0), ent_begin((size_t)G * (rows_max + 1), 0), warp_ent((size_t)G * (kWarps + 1), 0),
+        owner(Nk, 0);
+    L.ent_max = 1; L.went_max = 1;
+    std::vector<Term> terms;
+    for (int c = 0; c < G; c++) {
+        int *dc = desc.data() + (size_t)c * cta_slots;
+        const int nrows = row0[c + 1] - row0[c];
+        std::vector<int> group_row;     // local row of every group of this CTA
+        for (int lr = 0; lr < nrows; lr++) {
+            const int r = row0[c] + lr;
+            owner[r] = c;
+            row_terms(Nk, r + 1, sym, terms);
+            const int gs = (int)group_row.size(), ngr = ((int)terms.size() + 31) / 32;
+            for (int g = 0; g < ngr; g++) group_row.push_back(lr);
+            for (size_t i = 0; i < terms.size(); i++)
+                dc[(size_t)gs * 32 + i] = terms[i].a | (terms[i].b << kDescIdxBits) | (terms[i].coef << kDescCoefShift) | kDescValid;
         }
-        L.xbuf_words = 16 * G + 16 * LF * G;
-        MCT_CUDA(cudaMalloc(&L.d_kslot, Nk * sizeof(int)));
-        MCT_CUDA(cudaMemcpy(L.d_kslot, kslot.data(), Nk * sizeof(int), cudaMemcpyHostToDevice));
+        const int GC = (int)group_row.size();
+        MCT_REQUIRE(GC <= kWarps * T, MCT_CUDA_ERROR, "internal: layout overflow");
+        // entries: (warp,row) pairs in group order
+        int n_ent = 0, prev_row = -1;
+        for (int lr = 0; lr <= nrows; lr++) ent_begin[(size_t)c * (rows_max + 1) + lr] = 0;
+        for (int w = 0; w < kWarps; w++) {
+            warp_ent[(size_t)c * (kWarps + 1) + w] = n_ent;
+            int prev = -1, nw = 0;
+            for (int j = 0; j < T; j++) {
+                const int g = w * T + j;
+                if (g >= GC) break;
+                const int lr = group_row[g];
+                if (lr != prev) {
+                    if (prev >= 0) for (int l = 0; l < 32; l++) dc[(size_t)g * 32 + l] |= kDescNewEntry;
+                    if (lr != prev_row) {   // first entry of this row: rows before it (if any were skipped) start here too
+                        for (int q = prev_row + 1; q <= lr; q++) ent_begin[(size_t)c * (rows_max + 1) + q] = n_ent;
+                        prev_row = lr;
+                    }
+                    n_ent++; nw++; prev = lr;
+                }
+            }
+            L.went_max = std::max(L.went_max, nw);
+        }
+        warp_ent[(size_t)c * (kWarps + 1) + kWarps] = n_ent;
+        for (int q = prev_row + 1; q <= rows_max; q++) ent_begin[(size_t)c * (rows_max + 1) + q] = n_ent;
+        L.ent_max = std::max(L.ent_max, n_ent);
+        meta[4 * c] = row0[c]; meta[4 * c + 1] = nrows; meta[4 * c + 2] = n_ent;
     }
-    MCT_CUDA(cudaMalloc(&L.d_tasks, std::max<size_t>(1, tasks.size()) * sizeof(Task)));
-    MCT_CUDA(cudaMemcpy(L.d_tasks, tasks.data(), tasks.size() * sizeof(Task), cudaMemcpyHostToDevice));
-    MCT_CUDA(cudaMalloc(&L.d_task_begin, task_begin.size() * sizeof(int)));
-    MCT_CUDA(cudaMemcpy(L.d_task_begin, task_begin.data(), task_begin.size() * sizeof(int), cudaMemcpyHostToDevice));
-    MCT_CUDA(cudaMalloc(&L.d_rows, rows.size() * sizeof(int)));
-    MCT_CUDA(cudaMemcpy(L.d_rows, rows.data(), rows.size() * sizeof(int), cudaMemcpyHostToDevice));
-    MCT_CUDA(cudaMalloc(&L.d_row_slot, row_slot.size() * sizeof(int)));
-    MCT_CUDA(cudaMemcpy(L.d_row_slot, row_slot.data(), row_slot.size() * sizeof(int), cudaMemcpyHostToDevice));
-    MCT_CUDA(cudaMalloc(&L.d_cta_off, L.cta_off.size() * sizeof(long long)));
-    MCT_CUDA(cudaMemcpy(L.d_cta_off, L.cta_off.data(), L.cta_off.size() * sizeof(long long), cudaMemcpyHostToDevice));
-    MCT_CUDA(cudaMalloc(&L.d_pieces, L.pieces.size() * sizeof(Piece)));
-    MCT_CUDA(cudaMemcpy(L.d_pieces, L.pieces.data(), L.pieces.size() * sizeof(Piece), cudaMemcpyHostToDevice));
+    L.xbuf_words = 4 * G + ((Nk + 15) / 16) * 16 + 16;
+    auto up = [](int **dst, const std::vector<int> &v) {
+        cudaError_t e = cudaMalloc(dst, std::max<size_t>(1, v.size()) * sizeof(int));
+        if (e == cudaSuccess) e = cudaMemcpy(*dst, v.data(), v.size() * sizeof(int), cudaMemcpyHostToDevice);
+        return e;
+    };
+    MCT_CUDA(up(&L.d_desc, desc));
+    MCT_CUDA(up(&L.d_cta_meta, meta));
+    MCT_CUDA(up(&L.d_ent_begin, ent_begin));
+    MCT_CUDA(up(&L.d_warp_ent, warp_ent));
+    MCT_CUDA(up(&L.d_row_owner, owner));
     return MCT_OK;
 }
 
 void layout_free(TeamLayout &L) {
-    cudaFree(L.d_tab); cudaFree(L.d_tasks); cudaFree(L.d_task_begin); cudaFree(L.d_rows); cudaFree(L.d_row_slot);
-    cudaFree(L.d_cta_off); cudaFree(L.d_pieces); cudaFree(L.d_kslot);
+    cudaFree(L.d_desc); cudaFree(L.d_cta_meta); cudaFree(L.d_ent_begin); cudaFree(L.d_warp_ent); cudaFree(L.d_row_owner);
     L = TeamLayout();
 }
 
 int layout_fill_from_tables(const TeamLayout &L, double *d_tab, const double *dV1, const double *dV2, const double *dV3,
                             cudaStream_t s) {
-    fill_from_tables_kernel<<<L.n_pieces, 128, 0, s>>>(L.Nk, L.total_terms, L.d_pieces, dV1, dV2, dV3, d_tab);
+    const unsigned nb = (unsigned)((L.slab_terms + 255) / 256);
+    fill_from_tables_kernel<<<nb, 256, 0, s>>>(L.Nk, L.slab_terms, L.d_desc, dV1, dV2, dV3, d_tab);
     MCT_CUDA(cudaGetLastError());
     return MCT_OK;
 }
@@ -231,8 +241,8 @@ int layout_fill_from_sk(const TeamLayout &L, double *d_tab, const double *dk_arr
     MCT_CUDA(cudaMemcpyAsync(k01, dk_array, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
     MCT_CUDA(cudaStreamSynchronize(s));
     double dk = k01[1] - k01[0];
-    fill_from_sk_kernel<<<L.n_pieces, 128, 0, s>>>(L.Nk, L.total_terms, L.d_pieces, dk_array, dCk, rho, D0, pi2c, dk, tagged,
-                                                   d_tab);
+    const unsigned nb = (unsigned)((L.slab_terms + 255) / 256);
+    fill_from_sk_kernel<<<nb, 256, 0, s>>>(L.Nk, L.slab_terms, L.d_desc, dk_array, dCk, rho, D0, pi2c, dk, tagged, d_tab);
     MCT_CUDA(cudaGetLastError());
     return MCT_OK;
 }

@@ -4,58 +4,47 @@
 //                                            - sum_{iq<ik} A_m[iq,ik-iq],     A_m[iq,ip] = V_m[iq,ip] F1[iq] F2[ip]
 // (src/Kernels/ModeCouplingKernels.jl:154-208) by walking diagonals and antidiagonals of three Nk x Nk
 // column-major matrices with stride Nk+-1.  Here every "row" ik owns the terms of its increment
-// inc_m[ik] = T_m[ik]-T_m[ik-1]; the terms of a row are stored CONTIGUOUSLY, pre-multiplied by their sign
-// (and by 2 where the symmetric form merges A[q,p]+A[p,q]), so that a warp streams them with unit stride.
-// Rows are dealt to the G CTAs of a team in snake order (cost of row ik falls linearly with ik), each CTA's
-// slab is what it keeps resident in shared memory for the whole solve.
+// inc_m[ik] = T_m[ik]-T_m[ik-1].  A term is (a, b, coef): it contributes coef * V_m[a,b] * F1[a] * F2[b]; the
+// coefficient (+1, +2, -1, -2; 2 where the symmetric form merges A[q,p]+A[p,q]) is folded into the stored table
+// value.  The terms of a row are padded to a multiple of 32 ("groups": one term per lane of a warp), rows are
+// dealt to the G CTAs of a team as contiguous, cost-balanced ranges, and the groups of a CTA are split evenly
+// over its 16 warps: warp w of CTA c streams groups [w*T, (w+1)*T) of the CTA's group sequence.  The slab of a
+// CTA (16*T*32 term slots per table) is what the CTA keeps resident in registers + shared memory for the whole
+// solve; every thread owns the fixed slots  (w*T + j)*32 + lane,  j < T.
 #pragma once
 #include "common.cuh"
 
 namespace mct {
 
-struct Task {      // a run of consecutive terms of one row, executed by one warp (32 bytes)
-    int a0;        // index into F1 of the first term (0-based)
-    int b0;        // index into F2 of the first term (0-based)
-    int bdir;      // F2 index step per term: +1 (diagonals) or -1 (antidiagonals); F1 always steps +1
-    int len;       // number of terms
-    int off;       // offset of the first term inside the CTA slab
-    int slot;      // partial-sum slot inside the CTA (shared by consecutive tasks of one row in one warp)
-    int where;     // 0: slab part resident in shared memory, 1: part spilled to global (L2)
-    int flush;     // 1: last task of its slot -> reduce across the warp and store the partial sum
-};
-
-struct Piece {     // a run of terms of one row, used to build the slab from the Nk x Nk tables
-    int a0, b0, bdir, len;
-    long long off;  // global term offset inside the layout
-    double coef;    // +1, +2, -1, -2
-};
+// packed per-slot descriptor (one int per thread and group)
+constexpr int kDescIdxBits = 11;                 // Nk <= 2048
+constexpr int kDescIdxMask = (1 << kDescIdxBits) - 1;
+constexpr int kDescCoefShift = 22;               // 2 bits: 0:+1 1:+2 2:-1 3:-2
+constexpr int kDescValid = 1 << 24;              // slot holds a term (otherwise the table value is 0)
+constexpr int kDescNewEntry = 1 << 25;           // warp-uniform: this group starts a new (warp,row) entry
 
 struct TeamLayout {
     int Nk = 0, G = 0, sym = 0;
-    int smem_terms = 0;    // per-CTA capacity (terms) of the shared-memory resident part
-    int rows_max = 0;      // max rows per CTA
-    int slots_max = 0;     // max partial-sum slots per CTA
-    int tasks_max = 0;     // max tasks of one warp
-    long long total_terms = 0;
-    std::vector<long long> cta_off;  // [G+1]
+    int T = 0;             // groups per warp
+    int rows_max = 0;      // max rows owned by one CTA
+    int ent_max = 0;       // max (warp,row) entries of one CTA
+    int went_max = 0;      // max entries of one warp
+    long long slab_terms = 0;   // G*16*T*32: stride between the three tables
     // device copies
-    double *d_tab = nullptr;      // [3][total_terms]
-    Task *d_tasks = nullptr;      // all tasks, grouped by (cta, warp)
-    int *d_task_begin = nullptr;  // [G*kWarps + 1]
-    int *d_rows = nullptr;        // [G][rows_max]   row index ik (0-based) or -1
-    int *d_row_slot = nullptr;    // [G][rows_max+1] slot range of each local row
-    long long *d_cta_off = nullptr;  // [G+1]
-    int *d_kslot = nullptr;          // [Nk] word offset of wavenumber k's slot in an exchange buffer
-    int xbuf_words = 0;              // words (doubles) of one exchange buffer
-    std::vector<Piece> pieces;    // host copy (kept for building more slabs with the same geometry)
-    Piece *d_pieces = nullptr;
-    int n_pieces = 0;
+    int *d_desc = nullptr;       // [G][16][T][32]
+    int *d_cta_meta = nullptr;   // [G][4]: row0, nrows, n_entries, 0
+    int *d_ent_begin = nullptr;  // [G][rows_max+1]: entry range of each owned row
+    int *d_warp_ent = nullptr;   // [G][16]: first entry of each warp
+    int *d_row_owner = nullptr;  // [Nk]: owner CTA of each row
+    int xbuf_words = 0;          // words (doubles) of one exchange buffer
 };
 
-// Geometry only (no table values): depends on (Nk, G, sym, smem_terms).
-int layout_build_geometry(TeamLayout &L, int Nk, int G, int sym, int smem_terms);
+// Geometry only (no table values): depends on (Nk, G, sym).
+int layout_build_geometry(TeamLayout &L, int Nk, int G, int sym);
 void layout_free(TeamLayout &L);
-// Fill L.d_tab (must be allocated, 3*total_terms doubles) from column-major device tables.
+// groups per warp the geometry (Nk, G, sym) would have, without building it
+int layout_groups_per_warp(int Nk, int G, int sym, int *rows_max);
+// Fill d_tab (3*slab_terms doubles) from column-major device tables.
 int layout_fill_from_tables(const TeamLayout &L, double *d_tab, const double *dV1, const double *dV2, const double *dV3,
                             cudaStream_t s);
 // Fill from S(k) directly, evaluating the reference constructor's expressions in their own order

@@ -7,7 +7,7 @@ namespace mct {
 
 // One memory equation resident on the device (all arrays length Nk unless noted).
 struct EqDev {
-    const double *tab;      // team-layout vertex tables [3][total_terms]
+    const double *tab;      // team-layout vertex tables [3][slab_terms]
     const double *kvec;     // wavenumbers
     const double *alpha, *beta, *gamma, *delta;  // coefficients expanded to per-k values
     const double *F0, *dF0;
@@ -19,32 +19,45 @@ struct EqDev {
     long long *kernel_evals;
 };
 
+// byte offsets of the kernel's arrays inside its dynamic shared memory (filled by td_sc_launch; kept in the
+// parameter bank so that they cost no registers)
+struct SmemOffsets {
+    unsigned F1, F2, rho, off, wt, own, part, lane, C, X, scan, misc, eq, desc, tab, total;
+};
+
 struct SolveParams {
     int Nk, G, N, nblocks, n_eq, nteams, second_order;
     double dt0, tol;
     long long max_iter;
-    // layout geometry shared by every equation of the launch
-    long long total_terms;
-    const long long *cta_off;
-    const Task *tasks;
-    const int *task_begin;
-    const int *rows;
-    const int *row_slot;
-    const int *kslot;           // [Nk] exchange-slot word of every wavenumber
-    int xbuf_words;             // words of one exchange buffer
-    int rows_max, slots_max, tasks_max, smem_terms;
+    // layout geometry shared by every equation of the launch (layout.cuh)
+    int T;                      // groups per warp
+    int TR;                     // groups per warp resident in registers (selects the kernel instantiation)
+    int TS;                     // groups per warp resident in shared memory; the remaining T-TR-TS stream from L2
+    int rows_max, ent_max, lane_cap;
+    long long slab_terms;
+    const int *desc, *cta_meta, *ent_begin, *warp_ent, *row_owner;
     // team communication
-    double *xbuf;               // [nteams][xstride]: four rotating exchange buffers of 3*Nk self-validating slots
-    long long xstride;
+    double *xbuf;               // [nteams][4][xbuf_words]: rotating exchange buffers of self-validating 8-byte slots
+    int xbuf_words;
+    long long xstride;          // doubles per team: 4*xbuf_words + 16 (arrival counter)
+    int poll_delay;             // ns between publishing and the first collecting load
+    int poll_backoff;           // ns between two collecting attempts
     int *queue;                 // next equation to solve
+    double *qbox;               // [nteams][4*16]: rotating mailbox for the equation index
     int *abort_flag;
     const EqDev *eqs;
     long long spin_limit_cycles;
-    long long *prof;            // [nteams][10] phase cycle counters (only filled when built with -DMCT_PROFILE)
+    SmemOffsets so;             // filled by td_sc_launch
+    int dbg;                    // debug switches of profile builds (MCT_DBG)
+    long long *prof;            // [G][16] phase cycle counters of team 0 (only filled when built with -DMCT_PROFILE)
 };
 
-size_t td_sc_smem_bytes(int Nk, int G, int slots_max, int tasks_max, int rows_max, int smem_terms);
-int td_sc_max_smem_terms(int Nk, int G, int slots_max_guess, int tasks_max_guess, int rows_max, size_t smem_limit);
+constexpr int kProfSlots = 32;
+
+// shared memory needed by a launch with these parameters; TS = 0 gives the fixed part
+size_t td_sc_smem_bytes(const SolveParams &P);
+// largest TR the kernel is instantiated for
+int td_sc_max_reg_groups();
 int td_sc_launch(const SolveParams &P, cudaStream_t stream);
 
 }  // namespace mct
