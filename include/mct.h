@@ -47,6 +47,7 @@ typedef struct mct_equation_s *mct_equation_t; /* a MemoryEquation resident on t
 MCT_API const char *mct_last_error(void); /* message of the last failing call on this thread */
 MCT_API int mct_device_count(int *count);
 MCT_API int mct_version(void);
+MCT_API long mct_launch_count(void); /* CUDA kernels launched by this library in this process so far (benchmark evidence) */
 
 /* ---- memory kernels: plug-in point #2, `evaluate_kernel!(out, kernel, F, t)`  src/Kernels.jl:10-26 ---- */
 

@@ -49,7 +49,7 @@ class Coeffs(C.Structure):
 
 
 EXPORTS = [
-    "mct_last_error", "mct_device_count", "mct_version", "mct_sc3d_create", "mct_sc3d_create_from_sk",
+    "mct_last_error", "mct_device_count", "mct_version", "mct_launch_count", "mct_sc3d_create", "mct_sc3d_create_from_sk",
     "mct_sc3d_tagged_create", "mct_sc3d_tagged_create_from_sk", "mct_sc3d_tagged_create_from_equation", "mct_mc3d_create",
     "mct_ddim_create", "mct_kernel_eval", "mct_kernel_eval_many", "mct_kernel_destroy", "mct_td_output_len", "mct_td_solve",
     "mct_equation_create", "mct_equation_solve", "mct_equation_download", "mct_equation_destroy", "mct_equation_solve_batch",
@@ -69,6 +69,7 @@ def load_library():
             raise MCTDeviceError(f"{_LIB_PATH} is missing: run `python __graft_entry__.py build` (there is no CPU fallback)")
         L = C.CDLL(_LIB_PATH)
         L.mct_last_error.restype = C.c_char_p
+        L.mct_launch_count.restype = C.c_long
         _lib = L
     return _lib
 
@@ -95,6 +96,11 @@ def _arr(a, shape=None):
 
 def _p(a):
     return a.ctypes.data_as(c_dp)
+
+
+def launch_count():
+    """CUDA kernels launched by libmct_sm100a.so in this process so far."""
+    return load_library().mct_launch_count()
 
 
 def device_count():
@@ -354,6 +360,33 @@ def solve(equation, solver=None, keep_device=True):
     if not keep_device:
         dev_eq.close()
     return sol
+
+
+def create_equation(equation, solver):
+    """Upload an equation once (coefficients, initial conditions; allocates rings + trajectory on the device)."""
+    return _create_equation(equation, solver)
+
+
+def solve_resident(dev_eq):
+    """Run the persistent kernel on an equation that is already resident (no host<->device traffic).
+    Returns (kernel_evals, device_ms)."""
+    evals = C.c_long(0)
+    ms = C.c_float(0)
+    _check(load_library().mct_equation_solve(dev_eq._q, C.byref(evals), C.byref(ms)))
+    return evals.value, ms.value
+
+
+def solve_into(equation, solver, t, F, K):
+    """solve(equation, solver) through the one-call C entry point `mct_td_solve` with caller-owned HOST buffers
+    (t[nt], F[nt, dof], K[nt, dof]) -- what the Julia glue ccalls."""
+    c = equation._c_coeffs()
+    o = solver._c_opts()
+    evals = C.c_long(0)
+    rc = load_library().mct_td_solve(equation.kernel._h, C.byref(c), _p(equation.F0), _p(equation.dF0), C.byref(o), _p(t), _p(F),
+                                     _p(K), C.byref(evals))
+    solver.kernel_evals = evals.value
+    _check(rc)
+    return MemoryEquationSolution(t, F, K, solver)
 
 
 def solve_batch(equations, solver=None, download=True):

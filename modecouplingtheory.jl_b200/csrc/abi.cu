@@ -1,5 +1,6 @@
 // abi.cu -- the extern "C" boundary declared in include/mct.h.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -15,6 +16,8 @@
 namespace mct {
 
 static thread_local std::string g_last_error;
+static std::atomic<long> g_launches{0};
+void count_launch(int n) { g_launches += n; }
 void set_error(const std::string &msg) { g_last_error = msg; }
 int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
     char buf[512];
@@ -427,6 +430,7 @@ extern "C" {
 
 const char *mct_last_error(void) { return g_last_error.c_str(); }
 int mct_version(void) { return 100; }
+long mct_launch_count(void) { return g_launches.load(); }
 
 int mct_device_count(int *count) {
     MCT_REQUIRE(count != nullptr, MCT_BAD_ARGUMENT, "count is NULL");

@@ -11,6 +11,7 @@
 namespace mct {
 
 void set_error(const std::string &msg);
+void count_launch(int n = 1);   // every kernel launch of this library (reported by mct_launch_count)
 int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
 
 #define MCT_CUDA(call)                                                            \

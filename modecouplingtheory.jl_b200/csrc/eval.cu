@@ -119,6 +119,7 @@ int sc3d_eval_launch(int Nk, int n, const double *dk, const double *dV1, const d
     if (KPT <= 1) sc3d_finalize<1><<<n, kThreads, 0, s>>>(Nk, nseg, dk, d_scratch, d_out);
     else if (KPT <= 2) sc3d_finalize<2><<<n, kThreads, 0, s>>>(Nk, nseg, dk, d_scratch, d_out);
     else sc3d_finalize<4><<<n, kThreads, 0, s>>>(Nk, nseg, dk, d_scratch, d_out);
+    count_launch(2);
     MCT_CUDA(cudaGetLastError());
     return MCT_OK;
 }

@@ -224,6 +224,7 @@ int layout_fill_from_tables(const TeamLayout &L, double *d_tab, const double *dV
                             cudaStream_t s) {
     const unsigned nb = (unsigned)((L.slab_terms + 255) / 256);
     fill_from_tables_kernel<<<nb, 256, 0, s>>>(L.Nk, L.slab_terms, L.d_desc, dV1, dV2, dV3, d_tab);
+    count_launch();
     MCT_CUDA(cudaGetLastError());
     return MCT_OK;
 }
@@ -243,6 +244,7 @@ int layout_fill_from_sk(const TeamLayout &L, double *d_tab, const double *dk_arr
     double dk = k01[1] - k01[0];
     const unsigned nb = (unsigned)((L.slab_terms + 255) / 256);
     fill_from_sk_kernel<<<nb, 256, 0, s>>>(L.Nk, L.slab_terms, L.d_desc, dk_array, dCk, rho, D0, pi2c, dk, tagged, d_tab);
+    count_launch();
     MCT_CUDA(cudaGetLastError());
     return MCT_OK;
 }
@@ -256,9 +258,11 @@ int tables_from_sk(int Nk, const double *dk_array, const double *dSk, double *dC
     MCT_CUDA(cudaStreamSynchronize(s));
     double dk = k01[1] - k01[0];
     direct_correlation_kernel<<<(Nk + 127) / 128, 128, 0, s>>>(Nk, dSk, rho, dCk);
+    count_launch();
     if (dV1) {
         dim3 grid((Nk + 127) / 128, Nk);
         raw_tables_kernel<<<grid, 128, 0, s>>>(Nk, dk_array, dCk, rho, D0, pi2c, dk, tagged, dV1, dV2, dV3);
+        count_launch();
     }
     MCT_CUDA(cudaGetLastError());
     return MCT_OK;

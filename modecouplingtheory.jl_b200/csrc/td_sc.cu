@@ -845,6 +845,7 @@ int td_sc_launch(const SolveParams &P, cudaStream_t stream) {
     } else {
         MCT_CUDA(cudaLaunchKernel(fn, grid, block, args, smem, stream));
     }
+    count_launch();
     return MCT_OK;
 }
 
