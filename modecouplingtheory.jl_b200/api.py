@@ -207,6 +207,83 @@ def TaggedModeCouplingKernel(rho, kBT, m, k_array, Sk, sol, dims=3, device=0, ta
     return MemoryKernel(h, len(k), 1, device)
 
 
+def _to_blocks(X):
+    """[Nk, ns, ns] arrays X[k][a, b] (numpy row-major) -> flat [Nk][ns*ns] column-major blocks, the memory of a Julia
+    Vector{SMatrix{Ns,Ns}}.  Flat input passes through."""
+    X = np.asarray(X, dtype=np.float64)
+    if X.ndim == 3:
+        return np.ascontiguousarray(np.transpose(X, (0, 2, 1))).reshape(-1)
+    return np.ascontiguousarray(X).reshape(-1)
+
+
+def _from_blocks(flat, Nk, ns):
+    """inverse of _to_blocks for one or many time points: [..., Nk*ns*ns] -> [..., Nk, ns, ns] with [a, b] indexing."""
+    a = np.asarray(flat).reshape(flat.shape[:-1] + (Nk, ns, ns))
+    return np.swapaxes(a, -1, -2)
+
+
+def MultiComponentModeCouplingKernel(rho, kBT, m, k_array, Sk, dims=3, device=0):
+    """MultiComponentModeCouplingKernel(ρ, kBT, m, k_array, Sₖ; dims=3) -- src/Kernels/MultiComponentKernels.jl:84-131.
+    `Sk[k]` is the Ns x Ns matrix S_αβ(k)/sqrt(x_α x_β) as in the reference.  The constructor's host work (direct
+    correlation blocks C[k] = (δ./x - inv(S[k]))/ρ_all :103-109, prefactor :122-127) is done here like in Julia; the
+    kernel evaluation and everything that consumes it runs on the device."""
+    if dims != 3:
+        raise NotImplementedError("MSD is not implemented for dimentions other than 3")
+    L = load_library()
+    k = _arr(k_array)
+    rho = _arr(rho); m = _arr(m)
+    Sk = np.asarray(Sk, dtype=np.float64)
+    Nk, ns = len(k), len(rho)
+    assert Sk.shape == (Nk, ns, ns) and m.shape == rho.shape
+    dk = k[1] - k[0]
+    rho_all = rho.sum()
+    x = rho / rho.sum()
+    Sinv = np.linalg.inv(Sk)
+    Ck = (np.eye(ns)[None, :, :] / x[None, :, None] - Sinv) / rho_all
+    pref = np.empty((ns, ns))
+    for a in range(ns):
+        for b in range(ns):
+            pref[a, b] = rho_all * kBT / (8 * m[a] * x[b]) * (dk / 2 / np.pi) ** 2
+    Cb = _to_blocks(Ck)
+    pb = np.ascontiguousarray(pref.T).reshape(-1)            # column-major
+    h = C.c_void_p()
+    _check(L.mct_mc3d_create(C.byref(h), device, Nk, ns, _p(k), _p(Cb), _p(pb)))
+    return MemoryKernel(h, Nk, ns, device)
+
+
+def _surface_d_dim_unit_sphere(d):
+    from math import gamma, pi
+    return 2 * pi ** (d / 2) / gamma(d / 2)
+
+
+def ddim_tables(rho, kBT, m, k_array, Sk, d):
+    """prefactor, V[iq, ik, ip], J[iq, ik, ip] of dDimModeCouplingKernel -- src/Kernels/ModeCouplingKernels.jl:34-71."""
+    k = _arr(k_array); Sk = _arr(Sk)
+    Nk = len(k)
+    dk = k[1] - k[0]
+    Ck = (1 - 1.0 / Sk) / rho
+    prefactor = (kBT / m) * rho * dk ** 2 * _surface_d_dim_unit_sphere(d - 1) / (4 * np.pi) ** d
+    iq, ik, ip = np.meshgrid(np.arange(1, Nk + 1), np.arange(1, Nk + 1), np.arange(1, Nk + 1), indexing="ij")
+    q, kk, p = k[iq - 1], k[ik - 1], k[ip - 1]
+    c_p, c_k = Ck[ip - 1], Ck[ik - 1]
+    inside = (np.abs(iq - ik) + 1 <= ip) & (ip <= np.minimum(Nk, ik + iq - 1))
+    base = np.where(inside, 4 * q ** 2 * kk ** 2 - (q ** 2 + kk ** 2 - p ** 2) ** 2, 1.0)
+    J = np.where(inside, kk * p * base ** ((d - 3) / 2) / q ** d, 0.0)
+    V = np.where(inside, ((q ** 2 + kk ** 2 - p ** 2) * c_k + (q ** 2 - kk ** 2 + p ** 2) * c_p) ** 2, 0.0)
+    return prefactor, np.asfortranarray(V), np.asfortranarray(J)
+
+
+def dDimModeCouplingKernel(rho, kBT, m, k_array, Sk, d, device=0):
+    """dDimModeCouplingKernel(ρ, kBT, m, k_array, Sₖ, d) -- src/Kernels/ModeCouplingKernels.jl:34-71.  The O(Nk^3)
+    tables are built on the host like in the Julia constructor and shipped once."""
+    L = load_library()
+    k = _arr(k_array)
+    prefactor, V, J = ddim_tables(rho, kBT, m, k, Sk, d)
+    h = C.c_void_p()
+    _check(L.mct_ddim_create(C.byref(h), device, len(k), _p(k), C.c_double(prefactor), _p(V), _p(J)))
+    return MemoryKernel(h, len(k), 1, device)
+
+
 def evaluate_kernel(kernel, F, t=0):
     """out = evaluate_kernel(kernel, F, t) -- src/Kernels.jl:18-26.  For tagged kernels `t` is the index of the time
     in the collective solution's `t` array."""
@@ -217,7 +294,7 @@ def evaluate_kernel(kernel, F, t=0):
 
 def evaluate_kernel_(out, kernel, F, t=0):
     """evaluate_kernel!(out, kernel, F, t) -- src/Kernels.jl:10-16."""
-    F = _arr(F, (kernel.dof,))
+    F = _arr(_to_blocks(F) if kernel.Ns > 1 else F, (kernel.dof,))
     assert out.dtype == np.float64 and out.flags.c_contiguous and out.size == kernel.dof
     _check(load_library().mct_kernel_eval(kernel._h, _p(F), C.c_long(int(t)), _p(out)))
     return out
@@ -242,13 +319,14 @@ class MemoryEquation:
         if update_coefficients is not None:
             raise NotImplementedError("update_coefficients! callbacks are not supported by the device solver")
         self.kernel = kernel
-        self.F0 = _arr(F0, (kernel.dof,))
-        self.dF0 = _arr(dF0, (kernel.dof,))
+        blk = _to_blocks if kernel.Ns > 1 else (lambda v: v)
+        self.F0 = _arr(blk(F0), (kernel.dof,))
+        self.dF0 = _arr(blk(dF0), (kernel.dof,))
         self.coeffs = {}
         for name, v in (("alpha", alpha), ("beta", beta), ("gamma", gamma)):
-            self.coeffs[name] = float(v) if np.isscalar(v) else _arr(v, (kernel.dof,))
+            self.coeffs[name] = float(v) if np.isscalar(v) else _arr(blk(v), (kernel.dof,))
         self.delta = None if (np.isscalar(delta) and float(delta) == 0.0) else (
-            np.full(kernel.dof, float(delta)) if np.isscalar(delta) else _arr(delta, (kernel.dof,)))
+            np.full(kernel.dof, float(delta)) if np.isscalar(delta) else _arr(blk(delta), (kernel.dof,)))
 
     def _c_coeffs(self):
         c = Coeffs()
@@ -416,8 +494,9 @@ def solve_batch(equations, solver=None, download=True):
 
 def solve_steady_state(gamma, F0, kernel, tolerance=1e-8, max_iterations=10 ** 6, verbose=False):
     """solve_steady_state(γ, F₀, kernel; tolerance, max_iterations) -- src/SteadyStateMemoryEquation.jl:49-100."""
-    g = _arr(gamma, (kernel.dof,)) if not np.isscalar(gamma) else np.full(kernel.dof, float(gamma))
-    F0 = _arr(F0, (kernel.dof,))
+    blk = _to_blocks if kernel.Ns > 1 else (lambda v: v)
+    g = _arr(blk(gamma), (kernel.dof,)) if not np.isscalar(gamma) else np.full(kernel.dof, float(gamma))
+    F0 = _arr(blk(F0), (kernel.dof,))
     F = np.empty(kernel.dof); K = np.empty(kernel.dof)
     it = C.c_long(0)
     rc = load_library().mct_steady_state(kernel._h, _p(g), _p(F0), C.c_double(tolerance), C.c_long(max_iterations), _p(F), _p(K),

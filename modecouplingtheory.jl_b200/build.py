@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libmct_sm100a.so")
-SOURCES = ["abi.cu", "layout.cu", "eval.cu", "td_sc.cu"]
+SOURCES = ["abi.cu", "layout.cu", "eval.cu", "td_sc.cu", "td_grid.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-fmad=false",            # reference-order arithmetic: FMAs only where the code asks for them with fma()

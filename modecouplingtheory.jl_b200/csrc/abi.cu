@@ -11,6 +11,7 @@
 #include "common.cuh"
 #include "eval.cuh"
 #include "layout.cuh"
+#include "td_grid.cuh"
 #include "td_sc.cuh"
 
 namespace mct {
@@ -45,6 +46,8 @@ struct mct_kernel_s {
     bool from_sk = false;
     double rho = 0, kBT = 0, m = 0;
     double *d_Sk = nullptr, *d_Ck = nullptr;
+    // multi-component: direct correlation blocks + prefactor; dDim: fused table
+    double *d_C = nullptr, *d_pref = nullptr, *d_W = nullptr;
     // tagged
     long nt = 0;
     double *d_Fc = nullptr;
@@ -65,6 +68,10 @@ struct mct_equation_s {
     int *d_status = nullptr;
     long long *d_evals = nullptr;
     bool solved = false;
+    // block-valued / dense kernels (td_grid.cu): one allocation holding coefficients and workspace
+    int ns = 1;
+    double *d_gws = nullptr;
+    GridParams gp{};
 };
 
 namespace mct {
@@ -423,6 +430,78 @@ static int run_batch(int n, mct_equation_t *eqs, int mode, double tol, long long
     return worst;
 }
 
+
+// ---- block-valued / dense kernels: everything goes through td_grid.cu ------------------------------------------
+static bool is_grid_kernel(const mct_kernel_s *h) { return h->type == K_MC3D || h->type == K_DDIM; }
+
+// per-k blocks [Nk][nb] of a multiplicative coefficient: UniformScaling -> lambda*I, Diagonal -> the blocks given
+static int expand_coef_blocks(int kind, double lam, const double *arr, int Nk, int ns, double *dst, const char *name) {
+    const int nb = ns * ns;
+    if (kind == 0) {
+        std::fill(dst, dst + (size_t)Nk * nb, 0.0);
+        for (int k = 0; k < Nk; k++) for (int a = 0; a < ns; a++) dst[(size_t)k * nb + a + a * ns] = lam;
+        return MCT_OK;
+    }
+    MCT_REQUIRE(kind == 1 && arr != nullptr, MCT_BAD_ARGUMENT, std::string("bad coefficient ") + name);
+    memcpy(dst, arr, (size_t)Nk * nb * sizeof(double));
+    return MCT_OK;
+}
+
+// Fills q->gp and allocates its workspace.  mode 0: time doubling (needs opts), 1: steady state, 2: one evaluation.
+static int grid_setup(mct_equation_t q, mct_kernel_t h, int mode, const std::vector<double> &coef_host /* [6][dof] */) {
+    const int Nk = h->Nk, ns = h->Ns, nb = ns * ns;
+    const size_t dof = (size_t)Nk * nb;
+    const int N = (mode == 0) ? q->opts.N : 1;
+    const size_t ring = (mode == 0) ? (size_t)4 * N * dof : 0;
+    const size_t traj = (mode == 0) ? (size_t)q->nt * dof : dof;
+    const size_t lsum = (size_t)3 * Nk * 3 * nb;
+    const size_t dfh = (mode == 0) ? (size_t)(2 * N + 1) * dof : 0;
+    const size_t total = 6 * dof + 4 * ring + 7 * dof + 3 * dof + lsum + dfh + 2 * traj + 16;
+    MCT_CUDA(cudaMalloc(&q->d_gws, total * sizeof(double)));
+    MCT_CUDA(cudaMemset(q->d_gws, 0, total * sizeof(double)));
+    MCT_CUDA(cudaMemcpy(q->d_gws, coef_host.data(), 6 * dof * sizeof(double), cudaMemcpyHostToDevice));
+    GridParams &g = q->gp;
+    g = GridParams{};
+    g.type = (h->type == K_MC3D) ? GK_MC3D : GK_DDIM; g.Nk = Nk; g.ns = ns; g.mode = mode;
+    g.kvec = h->d_k; g.C = h->d_C; g.pref = h->d_pref; g.W = h->d_W;
+    double *p = q->d_gws;
+    g.alpha = p; g.beta = p + dof; g.gamma = p + 2 * dof; g.delta = p + 3 * dof; g.F0 = p + 4 * dof; g.dF0 = p + 5 * dof; p += 6 * dof;
+    g.Ft = p; g.Kt = p + ring; g.FI = p + 2 * ring; g.KI = p + 3 * ring; p += 4 * ring;
+    g.C1 = p; g.C2 = p + dof; g.C3 = p + 2 * dof; g.Fold = p + 3 * dof; g.K0 = p + 4 * dof; g.Fcur = p + 5 * dof; g.Kcur = p + 6 * dof; p += 7 * dof;
+    g.G = p; p += 3 * dof;
+    g.Lsum = p; p += lsum;
+    g.dFh = p; p += dfh;
+    g.F_out = p; g.K_out = p + traj; p += 2 * traj;
+    g.err = (unsigned long long *)p; p += 2;
+    g.status = (int *)p; g.kernel_evals = (long long *)(p + 2);
+    q->d_F = g.F_out; q->d_K = g.K_out;
+    return MCT_OK;
+}
+
+static int grid_run(mct_equation_t q, long long *evals, int *status, float *device_ms) {
+    mct_kernel_t h = q->kernel;
+    MCT_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    MCT_CUDA(cudaMemsetAsync(q->gp.err, 0, 16 * sizeof(double), s));
+    cudaEvent_t e0, e1;
+    MCT_CUDA(cudaEventCreate(&e0)); MCT_CUDA(cudaEventCreate(&e1));
+    MCT_CUDA(cudaEventRecord(e0, s));
+    int rc = td_grid_launch(q->gp, h->n_sm, s);
+    if (rc) return rc;
+    MCT_CUDA(cudaEventRecord(e1, s));
+    MCT_CUDA(cudaStreamSynchronize(s));
+    float ms = 0.f;
+    MCT_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (device_ms) *device_ms = ms;
+    int st = 0; long long ev = 0;
+    MCT_CUDA(cudaMemcpy(&st, q->gp.status, sizeof(int), cudaMemcpyDeviceToHost));
+    MCT_CUDA(cudaMemcpy(&ev, q->gp.kernel_evals, sizeof(long long), cudaMemcpyDeviceToHost));
+    if (evals) *evals = ev;
+    if (status) *status = st;
+    return st;
+}
+
 }  // namespace mct
 
 // ================================================ extern "C" ================================================
@@ -492,20 +571,45 @@ int mct_sc3d_tagged_create_from_equation(mct_kernel_t *out, int Nk, double rho, 
     return MCT_OK;
 }
 
-int mct_mc3d_create(mct_kernel_t *, int, int, int, const double *, const double *, const double *) {
-    set_error("MultiComponentModeCouplingKernel3D is not implemented on the device yet");
-    return MCT_UNSUPPORTED;
+int mct_mc3d_create(mct_kernel_t *out, int device, int Nk, int Ns, const double *k_array, const double *Cblocks, const double *prefactor) {
+    MCT_REQUIRE(Ns >= 1 && Ns <= kNsMax, MCT_UNSUPPORTED, "the device supports 1 <= Ns <= 4 species");
+    MCT_REQUIRE(Cblocks && prefactor, MCT_BAD_ARGUMENT, "NULL argument to mct_mc3d_create");
+    int rc = new_handle(out, K_MC3D, device, Nk, k_array);
+    if (rc) return rc;
+    mct_kernel_t h = *out;
+    h->Ns = Ns;
+    const size_t nb = (size_t)Ns * Ns;
+    cudaError_t e = cudaMalloc(&h->d_C, (nb * Nk + nb) * sizeof(double));
+    if (e == cudaSuccess) { h->d_pref = h->d_C + nb * Nk; e = cudaMemcpyAsync(h->d_C, Cblocks, nb * Nk * sizeof(double), cudaMemcpyHostToDevice, h->stream); }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h->d_pref, prefactor, nb * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) { mct_kernel_destroy(h); *out = nullptr; return cuda_fail(e, "mct_mc3d_create", __FILE__, __LINE__); }
+    return MCT_OK;
 }
-int mct_ddim_create(mct_kernel_t *, int, int, const double *, double, const double *, const double *) {
-    set_error("dDimModeCouplingKernel is not implemented on the device yet");
-    return MCT_UNSUPPORTED;
+
+int mct_ddim_create(mct_kernel_t *out, int device, int Nk, const double *k_array, double prefactor, const double *V, const double *J) {
+    MCT_REQUIRE(V && J, MCT_BAD_ARGUMENT, "NULL argument to mct_ddim_create");
+    int rc = new_handle(out, K_DDIM, device, Nk, k_array);
+    if (rc) return rc;
+    mct_kernel_t h = *out;
+    const size_t n3 = (size_t)Nk * Nk * Nk;
+    double *tmp = nullptr;
+    cudaError_t e = cudaMalloc(&h->d_W, n3 * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&tmp, 2 * n3 * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(tmp, V, n3 * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(tmp + n3, J, n3 * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) { rc = ddim_build_table(Nk, prefactor, tmp, tmp + n3, h->d_W, h->stream); if (rc) e = cudaErrorUnknown; }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(tmp);
+    if (e != cudaSuccess) { mct_kernel_destroy(h); *out = nullptr; return rc ? rc : cuda_fail(e, "mct_ddim_create", __FILE__, __LINE__); }
+    return MCT_OK;
 }
 
 int mct_kernel_destroy(mct_kernel_t h) {
     if (!h) return MCT_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    cudaFree(h->d_k); cudaFree(h->d_V1); cudaFree(h->d_Sk);
+    cudaFree(h->d_k); cudaFree(h->d_V1); cudaFree(h->d_Sk); cudaFree(h->d_C); cudaFree(h->d_W);
     if (h->owns_Fc) cudaFree(h->d_Fc);
     for (auto &kv : h->slabs) cudaFree(kv.second);
     cudaFree(h->d_scratch); cudaFree(h->d_io);
@@ -543,8 +647,21 @@ int mct_kernel_eval_many(mct_kernel_t h, int n, const double *F, double *out, fl
 
 int mct_kernel_eval(mct_kernel_t h, const double *F, long t_index, double *out) {
     MCT_REQUIRE(h && F && out, MCT_BAD_ARGUMENT, "bad argument to mct_kernel_eval");
-    MCT_REQUIRE(h->type == K_SC3D || h->type == K_TAGGED3D, MCT_UNSUPPORTED, "kernel type not implemented on the device yet");
     MCT_CUDA(cudaSetDevice(h->device));
+    if (is_grid_kernel(h)) {
+        const size_t dof = (size_t)h->Nk * h->Ns * h->Ns;
+        mct_equation_s q;
+        q.kernel = h; q.Nk = h->Nk; q.ns = h->Ns; q.mode = 2; q.nt = 1;
+        std::vector<double> host(6 * dof, 0.0);
+        int rc = grid_setup(&q, h, 2, host);
+        double *dF = nullptr;
+        if (!rc) { cudaError_t e = cudaMalloc(&dF, dof * sizeof(double)); if (e == cudaSuccess) e = cudaMemcpy(dF, F, dof * sizeof(double), cudaMemcpyHostToDevice); if (e != cudaSuccess) rc = cuda_fail(e, "mct_kernel_eval", __FILE__, __LINE__); }
+        if (!rc) { q.gp.Fin = dF; rc = grid_run(&q, nullptr, nullptr, nullptr); }
+        if (!rc) { cudaError_t e = cudaMemcpy(out, q.gp.F_out, dof * sizeof(double), cudaMemcpyDeviceToHost); if (e != cudaSuccess) rc = cuda_fail(e, "mct_kernel_eval", __FILE__, __LINE__); }
+        cudaFree(dF); cudaFree(q.d_gws);
+        return rc;
+    }
+    MCT_REQUIRE(h->type == K_SC3D || h->type == K_TAGGED3D, MCT_UNSUPPORTED, "kernel type not implemented on the device yet");
     int rc = ensure_raw_tables(h);
     if (rc) return rc;
     const int Nk = h->Nk;
@@ -576,7 +693,7 @@ int mct_equation_create(mct_equation_t *out, mct_kernel_t h, const mct_coeffs *c
                         const mct_td_options *o) {
     MCT_REQUIRE(out && h && c && F0 && dF0 && o, MCT_BAD_ARGUMENT, "NULL argument to mct_equation_create");
     *out = nullptr;
-    MCT_REQUIRE(h->type == K_SC3D || h->type == K_TAGGED3D, MCT_UNSUPPORTED, "kernel type not implemented on the device yet");
+    MCT_REQUIRE(h->type == K_SC3D || h->type == K_TAGGED3D || is_grid_kernel(h), MCT_UNSUPPORTED, "kernel type not implemented on the device yet");
     MCT_REQUIRE(o->N >= 2 && o->dt > 0 && o->t_max > 0 && o->tolerance >= 0 && o->max_iterations >= 1, MCT_BAD_ARGUMENT,
                 "bad solver options");
     MCT_REQUIRE(o->init_with_memory == 1, MCT_UNSUPPORTED, "init_with_memory=false is not supported on the device");
@@ -589,6 +706,27 @@ int mct_equation_create(mct_equation_t *out, mct_kernel_t h, const mct_coeffs *c
         delete q;
         set_error("collective trajectory is shorter than this solve (tDict KeyError in the reference)");
         return MCT_BAD_ARGUMENT;
+    }
+    if (is_grid_kernel(h)) {
+        const int ns = h->Ns;
+        const size_t dof = (size_t)Nk * ns * ns;
+        q->ns = ns;
+        std::vector<double> host(6 * dof, 0.0);
+        int rc = expand_coef_blocks(c->alpha_kind, c->alpha_scalar, c->alpha, Nk, ns, host.data(), "alpha");
+        if (!rc) rc = expand_coef_blocks(c->beta_kind, c->beta_scalar, c->beta, Nk, ns, host.data() + dof, "beta");
+        if (!rc) rc = expand_coef_blocks(c->gamma_kind, c->gamma_scalar, c->gamma, Nk, ns, host.data() + 2 * dof, "gamma");
+        if (rc) { delete q; return rc; }
+        if (c->delta) memcpy(host.data() + 3 * dof, c->delta, dof * sizeof(double));
+        memcpy(host.data() + 4 * dof, F0, dof * sizeof(double));
+        memcpy(host.data() + 5 * dof, dF0, dof * sizeof(double));
+        q->second_order = 0;
+        for (size_t i = 0; i < dof; i++) if (host[i] != 0.0) q->second_order = 1;       // !iszero(alpha)  src/EulerSolver.jl:55
+        rc = grid_setup(q, h, 0, host);
+        if (rc) { mct_equation_destroy(q); return rc; }
+        q->gp.N = o->N; q->gp.nblocks = q->nblocks; q->gp.second_order = q->second_order;
+        q->gp.dt0 = o->dt; q->gp.tol = o->tolerance; q->gp.max_iter = o->max_iterations;
+        *out = q;
+        return MCT_OK;
     }
     std::vector<double> host(6 * (size_t)Nk);
     int rc = expand_coef(c->alpha_kind, c->alpha_scalar, c->alpha, Nk, host.data(), "alpha");
@@ -628,6 +766,7 @@ int mct_equation_create(mct_equation_t *out, mct_kernel_t h, const mct_coeffs *c
 int mct_equation_destroy(mct_equation_t q) {
     if (!q) return MCT_OK;
     if (q->kernel) cudaSetDevice(q->kernel->device);
+    if (q->d_gws) { cudaFree(q->d_gws); q->d_F = nullptr; }
     cudaFree(q->d_coef); cudaFree(q->d_ring); cudaFree(q->d_F); cudaFree(q->d_status);
     delete q;
     return MCT_OK;
@@ -636,6 +775,20 @@ int mct_equation_destroy(mct_equation_t q) {
 int mct_equation_solve_batch(int n, mct_equation_t *eqs, int *status, long *kernel_evals, float *device_ms) {
     MCT_REQUIRE(n >= 1 && eqs, MCT_BAD_ARGUMENT, "empty batch");
     for (int i = 0; i < n; i++) MCT_REQUIRE(eqs[i] && eqs[i]->mode == 0, MCT_BAD_ARGUMENT, "bad equation handle");
+    if (is_grid_kernel(eqs[0]->kernel)) {          // block-valued kernels: one cooperative launch per equation
+        int worst = MCT_OK;
+        float tot = 0.f;
+        for (int i = 0; i < n; i++) {
+            long e = 0; float ms = 0.f;
+            int rc = mct_equation_solve(eqs[i], &e, &ms);
+            if (status) status[i] = rc;
+            if (kernel_evals) kernel_evals[i] = e;
+            tot += ms;
+            if (rc != MCT_OK && worst == MCT_OK) worst = rc;
+        }
+        if (device_ms) *device_ms = tot;
+        return worst;
+    }
     std::vector<long long> ev(n, 0);
     int rc = run_batch(n, eqs, 0, eqs[0]->opts.tolerance, eqs[0]->opts.max_iterations, status, ev.data(), device_ms);
     if (kernel_evals) for (int i = 0; i < n; i++) kernel_evals[i] = (long)ev[i];
@@ -643,6 +796,17 @@ int mct_equation_solve_batch(int n, mct_equation_t *eqs, int *status, long *kern
 }
 
 int mct_equation_solve(mct_equation_t q, long *kernel_evals, float *device_ms) {
+    MCT_REQUIRE(q && q->kernel, MCT_BAD_ARGUMENT, "NULL equation");
+    if (is_grid_kernel(q->kernel)) {
+        long long ev = 0; int st = 0;
+        int rc = grid_run(q, &ev, &st, device_ms);
+        if (kernel_evals) *kernel_evals = (long)ev;
+        q->solved = (rc == MCT_OK);
+        if (rc == MCT_NOT_CONVERGED)
+            set_error("Iteration did not converge. Either increase the number of time steps before a time doubling, or choose a "
+                      "different memory kernel.");
+        return rc;
+    }
     int st = 0;
     long ev = 0;
     int rc = mct_equation_solve_batch(1, &q, &st, &ev, device_ms);
@@ -653,7 +817,7 @@ int mct_equation_solve(mct_equation_t q, long *kernel_evals, float *device_ms) {
 int mct_equation_download(mct_equation_t q, double *t_out, double *F_out, double *K_out) {
     MCT_REQUIRE(q, MCT_BAD_ARGUMENT, "NULL equation");
     MCT_CUDA(cudaSetDevice(q->kernel->device));
-    const size_t traj = (size_t)q->nt * q->Nk;
+    const size_t traj = (size_t)q->nt * q->Nk * q->ns * q->ns;
     if (F_out) MCT_CUDA(cudaMemcpy(F_out, q->d_F, traj * sizeof(double), cudaMemcpyDeviceToHost));
     if (K_out) MCT_CUDA(cudaMemcpy(K_out, q->d_K, traj * sizeof(double), cudaMemcpyDeviceToHost));
     if (t_out) {
@@ -686,8 +850,27 @@ int mct_td_solve(mct_kernel_t h, const mct_coeffs *c, const double *F0, const do
 int mct_steady_state(mct_kernel_t h, const double *gamma, const double *F0, double tolerance, long max_iterations,
                      double *F_out, double *K_out, long *iterations) {
     MCT_REQUIRE(h && gamma && F0 && F_out && K_out, MCT_BAD_ARGUMENT, "NULL argument to mct_steady_state");
-    MCT_REQUIRE(h->type == K_SC3D, MCT_UNSUPPORTED, "steady state is implemented for the collective single-component kernel");
     MCT_CUDA(cudaSetDevice(h->device));
+    if (is_grid_kernel(h)) {
+        const size_t dof = (size_t)h->Nk * h->Ns * h->Ns;
+        mct_equation_s q;
+        q.kernel = h; q.Nk = h->Nk; q.ns = h->Ns; q.mode = 1; q.nt = 1;
+        std::vector<double> host(6 * dof, 0.0);
+        memcpy(host.data() + 2 * dof, gamma, dof * sizeof(double));
+        memcpy(host.data() + 4 * dof, F0, dof * sizeof(double));
+        int rc = grid_setup(&q, h, 1, host);
+        long long it = 0;
+        if (!rc) { q.gp.tol = tolerance; q.gp.max_iter = max_iterations; rc = grid_run(&q, &it, nullptr, nullptr); }
+        if (rc == MCT_OK || rc == MCT_NOT_CONVERGED) {
+            cudaMemcpy(F_out, q.gp.F_out, dof * sizeof(double), cudaMemcpyDeviceToHost);
+            cudaMemcpy(K_out, q.gp.K_out, dof * sizeof(double), cudaMemcpyDeviceToHost);
+        }
+        if (iterations) *iterations = (long)it;
+        if (rc == MCT_NOT_CONVERGED) set_error("The recursive iteration did not converge.");
+        cudaFree(q.d_gws);
+        return rc;
+    }
+    MCT_REQUIRE(h->type == K_SC3D, MCT_UNSUPPORTED, "steady state is implemented for the collective single-component kernel");
     const int Nk = h->Nk;
     mct_equation_s q;
     q.kernel = h; q.Nk = Nk; q.mode = 1; q.nt = 1;

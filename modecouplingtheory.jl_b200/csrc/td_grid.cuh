@@ -1,0 +1,40 @@
+// td_grid.cuh -- whole-grid cooperative solver for the kernels whose degrees of freedom are Ns x Ns blocks per
+// wavenumber (MultiComponentModeCouplingKernel3D) or whose evaluation is a dense triple sum (dDimModeCouplingKernel).
+#pragma once
+#include "common.cuh"
+
+namespace mct {
+
+constexpr int kNsMax = 4;
+
+enum GridKernelType { GK_MC3D = 3, GK_DDIM = 5 };
+
+struct GridParams {
+    int type, Nk, ns, N, nblocks, second_order, mode;   // mode 0: time doubling, 1: steady state, 2: one evaluation
+    double dt0, tol;
+    long long max_iter;
+    // kernel data
+    const double *kvec;
+    const double *C, *pref;      // MC: direct correlation blocks [Nk][nb], prefactor [nb]
+    const double *W;             // dDim: prefactor * J .* V as [iq][ik][ip] (ip contiguous)
+    // equation: multiplicative coefficients as per-k blocks [Nk][nb]; delta, F0, dF0 [Nk][nb]
+    const double *alpha, *beta, *gamma, *delta, *F0, *dF0;
+    // workspace
+    double *Ft, *Kt, *FI, *KI;   // rings [4N][dof]  (slot s at index s-1)
+    double *C1, *C2, *C3, *Fold, *K0, *Fcur, *Kcur;   // [dof]
+    double *G;                   // MC: G1, G2, G3 [3][Nk][nb]
+    double *Lsum;                // line sums [3*Nk][3*nb]
+    double *dFh;                 // bootstrap: dF history [2N+1][dof]
+    unsigned long long *err;     // [2] rotating max-error words (bits of a non-negative double)
+    double *F_out, *K_out;       // trajectory [nt][dof]  (mode 1/2: [dof])
+    const double *Fin;           // mode 2: input F
+    int *status;
+    long long *kernel_evals;
+};
+
+int td_grid_launch(const GridParams &P, int n_sm, cudaStream_t stream);
+
+// dDim: fused table W[iq][ik][ip] = prefactor * J[iq,ik,ip] * V[iq,ik,ip] from the reference's column-major arrays
+int ddim_build_table(int Nk, double prefactor, const double *dV, const double *dJ, double *dW, cudaStream_t s);
+
+}  // namespace mct

@@ -1,0 +1,132 @@
+"""GPU parity of the block-valued and dense kernels (MultiComponentModeCouplingKernel3D, dDimModeCouplingKernel) and the
+solvers that consume them, through the C ABI, against the CPU oracle and the reference's goldens.
+
+Tolerances: the device sums the same numbers in a different order (line sums + prefix instead of the reference's
+sequential recursion; factorised species contraction, which the reference itself evaluates under @fastmath), so single
+evaluations are compared at rtol 1e-11 and solves at the north-star bound max|dF| <= 1e-10.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import oracle as O
+import problems as P
+from conftest import ROOT, load_pkg
+
+pytestmark = pytest.mark.gpu
+pkg = load_pkg()
+RTOL = 1.5e-8          # Julia's isapprox default, used by the reference's golden comparisons
+
+
+def mixture(ns, Nk=40, phi=0.45):
+    diam = np.linspace(0.7, 1.0, ns) if ns > 1 else np.array([1.0])
+    cr = np.arange(1, ns + 1, dtype=float); cr /= cr.sum()
+    rho = 6 * phi / (np.pi * np.sum(cr * diam ** 3)) * cr
+    k = P.sf.wavenumber_grid(Nk)
+    Sk = P.sf.percus_yevick_mixture_sk(k, diam, rho)
+    return rho, np.linspace(1.0, 1.5, ns), k, Sk
+
+
+@pytest.mark.parametrize("ns", [1, 2, 3, 4])
+def test_mc_eval_matches_oracle_and_brute_force(ns):
+    rho, m, k, Sk = mixture(ns)
+    Nk = len(k)
+    rng = np.random.default_rng(ns)
+    F = rng.random((Nk, ns, ns))
+    kern = pkg.MultiComponentModeCouplingKernel(rho, 1.3, m, k, Sk)
+    got = pkg.evaluate_kernel(kern, F)
+    ref = O.mc3d(rho, 1.3, m, k, Sk).evaluate(O._blocks(F))
+    scale = np.abs(ref).max()
+    assert np.max(np.abs(got - ref)) <= 1e-11 * scale
+    if ns <= 2:      # the reference's own cross-check: fast kernel == brute-force triangle sum (test/test_MCMCT.jl:192)
+        naive = O.mc3d(rho, 1.3, m, k, Sk, naive=True).evaluate(O._blocks(F))
+        assert np.allclose(got, naive, rtol=RTOL, atol=1e-12 * scale)
+
+
+def test_mc_time_doubling_golden_test_MCMCT_211():
+    b = P.binary_mixture()
+    Nk = b["Nk"]
+    kw = dict(N=4, dt=1e-4, t_max=1e3, tolerance=1e-12, max_iterations=20000)
+    kern = pkg.MultiComponentModeCouplingKernel(b["rho"], 1.0, b["m"], b["k"], b["Sk"])
+    eq = pkg.MemoryEquation(1.0, 0.0, b["gamma"], np.zeros((Nk, 2, 2)), b["Sk"], np.zeros((Nk, 2, 2)), kern)
+    solver = pkg.TimeDoublingSolver(**kw)
+    sol = pkg.solve(eq, solver)
+    Fend = sol.F[-1].reshape(Nk, 4)[18].reshape(2, 2, order="F")
+    gold = np.array([[0.13881069002073976, 0.04192527228732725], [0.041925272287327266, 0.52419581715369]])
+    assert np.allclose(Fend, gold, rtol=RTOL, atol=0)                                   # test/test_MCMCT.jl:211
+    ref = O.td_solve(O.mc3d(b["rho"], 1.0, b["m"], b["k"], b["Sk"]), 1.0, 0.0, O._blocks(b["gamma"]), np.zeros(Nk * 4),
+                     O._blocks(b["Sk"]), np.zeros(Nk * 4), **kw)
+    assert np.array_equal(sol.t, ref["t"])
+    assert np.max(np.abs(sol.F - ref["F"])) <= 1e-10
+    assert abs(solver.kernel_evals - ref["kernel_evals"]) <= 0.01 * ref["kernel_evals"]
+
+
+def test_mc_steady_state_golden_test_steady_state_104():
+    Nk = 100
+    diam = np.array([0.8, 1.0]); cr = np.array([0.2, 0.8]); cr /= cr.sum()
+    rho = 6 * 0.55 / (np.pi * np.sum(cr * diam ** 3)) * cr
+    x = rho / rho.sum()
+    k = P.sf.wavenumber_grid(Nk)
+    data = np.loadtxt(os.path.join(ROOT, "tests", "golden", "Sk_MC2.txt")).reshape(-1)
+    Sk = np.transpose(data.reshape((2, 2, 100), order="F") * np.sqrt(x[:, None, None] * x[None, :, None]), (2, 0, 1)).copy()
+    gam = np.einsum("kab,kbc->kac", np.array([np.diag(k[i] ** 2 * x) for i in range(Nk)]), np.linalg.inv(Sk))
+    kern = pkg.MultiComponentModeCouplingKernel(rho, 1.0, np.ones(2), k, Sk)
+    sol = pkg.solve_steady_state(gam, Sk, kern, tolerance=1e-12)
+    assert sol.F.sum() == pytest.approx(45.50146332163797, rel=RTOL)                     # test/test_steady_state.jl:104
+    ref = O.steady_state(O.mc3d(rho, 1.0, np.ones(2), k, Sk), O._blocks(gam), O._blocks(Sk), tolerance=1e-12)
+    assert np.max(np.abs(sol.F[0] - ref["F"]) / np.maximum(np.abs(ref["F"]), 1e-3)) < 1e-6
+
+
+def test_ddim_eval_matches_oracle_and_bengtzelius_at_d3():
+    p = P.hard_spheres(20, 0.50)
+    kd = pkg.dDimModeCouplingKernel(p["rho"], 1.0, 1.0, p["k"], p["Sk"], 3)
+    got = pkg.evaluate_kernel(kd, p["Sk"])
+    ref = O.ddim(p["rho"], 1.0, 1.0, p["k"], p["Sk"], 3).evaluate(p["Sk"])
+    assert np.max(np.abs(got - ref) / np.abs(ref)) < 1e-12
+    ks = pkg.evaluate_kernel(pkg.ModeCouplingKernel(p["rho"], 1.0, 1.0, p["k"], p["Sk"]), p["Sk"])
+    assert np.abs(got - ks).sum() < 1e-8                                                 # test/test_dDimMCT_consistency.jl:69
+    F = np.random.default_rng(5).random(20)
+    assert np.max(np.abs(pkg.evaluate_kernel(kd, F) - O.ddim(p["rho"], 1.0, 1.0, p["k"], p["Sk"], 3).evaluate(F)) / np.abs(ref)) < 1e-12
+
+
+def test_ddim_host_tables_are_bit_identical_to_oracle():
+    p = P.hard_spheres(16, 0.45)
+    for d in (2, 3, 5):
+        pref, V, J = pkg.ddim_tables(p["rho"], 1.0, 1.0, p["k"], p["Sk"], d)
+        Vo, Jo, po = O.ddim_tables(O.ddim(p["rho"], 1.0, 1.0, p["k"], p["Sk"], d))
+        assert np.allclose(V, Vo, rtol=1e-15, atol=0) and np.allclose(J, Jo, rtol=1e-14, atol=0) and pref == pytest.approx(po, rel=1e-15)
+
+
+def test_ddim_critical_point_2d_goldens_test_dDimMCT_crit_pt_96_97():
+    from scipy.special import j0, j1
+    k = P.sf.wavenumber_grid(100)
+
+    def ck2d(phi):
+        t1 = -5 * (1 - phi) ** 2 * k ** 2 * j0(k / 2) ** 2 / 4
+        t2 = (4 * ((phi - 20) * phi + 7) + 5 * (1 - phi) ** 2 * k ** 2 / 4) * j1(k / 2) ** 2
+        t3 = 2 * (phi - 13) * (1 - phi) * k * j1(k / 2) * j0(k / 2)
+        return np.pi * (t1 + t2 + t3) / (6 * (1 - phi) ** 3 * k ** 2)
+
+    out = {}
+    for phi in (0.69, 0.70):
+        rho = 4 * phi / np.pi
+        ck = ck2d(phi)
+        Sk = 1 + rho * ck / (1 - rho * ck)
+        kern = pkg.dDimModeCouplingKernel(rho, 1.0, 1.0, k, Sk, 2)
+        out[phi] = pkg.solve_steady_state(k ** 2 / Sk, Sk, kern, tolerance=1e-8).F.sum()
+    assert out[0.70] == pytest.approx(17.987734457716535, rel=RTOL)                      # test/test_dDimMCT_crit_pt.jl:96
+    assert out[0.69] < 1e-7                                                              # :97
+
+
+def test_ddim_time_doubling_vs_oracle():
+    p = P.hard_spheres(24, 0.50)
+    e = P.overdamped(p)
+    kw = dict(N=8, dt=1e-6, t_max=1e2, tolerance=1e-10)
+    kern = pkg.dDimModeCouplingKernel(p["rho"], 1.0, 1.0, p["k"], p["Sk"], 3)
+    eq = pkg.MemoryEquation(e["alpha"], e["beta"], e["gamma"], e["delta"], e["F0"], e["dF0"], kern)
+    solver = pkg.TimeDoublingSolver(**kw)
+    sol = pkg.solve(eq, solver)
+    ref = O.td_solve(O.ddim(p["rho"], 1.0, 1.0, p["k"], p["Sk"], 3), e["alpha"], e["beta"], e["gamma"], e["delta"], e["F0"], e["dF0"], **kw)
+    assert np.max(np.abs(sol.F - ref["F"])) <= 1e-10
+    assert abs(solver.kernel_evals - ref["kernel_evals"]) <= max(3, 0.01 * ref["kernel_evals"])
