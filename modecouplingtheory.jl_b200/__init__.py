@@ -4,7 +4,7 @@ Host-side mirror of the reference interface; all numerics run in libmct_sm100a.s
 behind a C ABI, include/mct.h).  There is no CPU fallback: calling into the library without the built
 extension or without a B200 raises MCTDeviceError.
 """
-from . import api, structure_factors  # noqa: F401
+from . import api, structure_factors, sweep  # noqa: F401
 from .api import (  # noqa: F401
     DomainError, MCTDeviceError, MemoryEquation, MemoryEquationSolution, MemoryKernel, ModeCouplingKernel,
     MultiComponentModeCouplingKernel, dDimModeCouplingKernel, ddim_tables,
