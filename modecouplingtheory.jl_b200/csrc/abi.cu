@@ -339,6 +339,7 @@ static int run_batch(int n, mct_equation_t *eqs, int mode, double tol, long long
     P.poll_delay = env_int("MCT_POLL_DELAY", 300);
     P.poll_backoff = env_int("MCT_POLL_BACKOFF", 100);
     P.dbg = env_int("MCT_DBG", 0);
+    P.snap_epoch = env_int("MCT_SNAP_EPOCH", 1000);
     P.spin_limit_cycles = (long long)env_int("MCT_SPIN_LIMIT_MS", 2000) * 2000000LL;
     if (env_int("MCT_VERBOSE", 0))
         fprintf(stderr, "[mct] Nk=%d sym=%d n_eq=%d: teams=%d x G=%d, T=%d groups/warp (TR=%d regs, TS=%d smem, %d L2), rows/CTA<=%d, smem=%zu B\n",
@@ -405,7 +406,7 @@ static int run_batch(int n, mct_equation_t *eqs, int mode, double tol, long long
             for (int c = 0; c < P.G; c++) {
                 fprintf(stderr, "  %3d", c);
                 for (int i = 19; i <= 23; i++) fprintf(stderr, " %6lld", pr[(size_t)c * kProfSlots + i] - t0);
-                fprintf(stderr, "   lanes 2-7:");
+                fprintf(stderr, "   |");
                 for (int i = 24; i < 30; i++) fprintf(stderr, " %6lld", pr[(size_t)c * kProfSlots + i] - t0);
                 fprintf(stderr, "\n");
             }

@@ -191,6 +191,9 @@ struct Team {
     // tid < nrows: L_m = sum of the increments of rows row0 .. row0+tid  (so T_m[k] = off_m(cta) + L_m).
     __device__ __forceinline__ void eval_rows(const double *__restrict__ gtab, double &L1, double &L2, double &L3) {
         PROF(8);
+#ifdef MCT_PROFILE
+        if (epoch + 1 == (unsigned)P.snap_epoch) { long long g__; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g__)); prof[24] = g__; }
+#endif
         {
             double a1 = 0.0, a2 = 0.0, a3 = 0.0;
             double *const sl0 = sLane + (size_t)warp * P.lane_cap * 3 * kLaneStride + lane;
@@ -240,6 +243,9 @@ struct Team {
         else block_inscan3(i1, i2, i3);
         L1 = i1; L2 = i2; L3 = i3;
         PROF(2);
+#ifdef MCT_PROFILE
+        if (epoch + 1 == (unsigned)P.snap_epoch) { long long g__; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g__)); prof[25] = g__; }
+#endif
     }
 
     // K = k T1 + T2/k^3 + T3/k   (:224-227) for the owned row, from the prefix inside the CTA and the CTA's offset
@@ -251,12 +257,11 @@ struct Team {
     }
 
     // ------------------------------------------------------------------------------------------ exchange
-    // offset of CTA c = prefix inside its warp of 32 CTAs + totals of the warps before it (fixed order)
+    // offset of CTA c (exclusive prefix of the block totals, written by the scanning warps of the last exchange)
     __device__ __forceinline__ void cta_offsets(int c, double &o1, double &o2, double &o3) const {
-        double b1 = 0.0, b2 = 0.0, b3 = 0.0;
-        for (int w = 0; w < (c >> 5); w++) { b1 += sWT[w]; b2 += sWT[8 + w]; b3 += sWT[16 + w]; }
-        o1 = b1 + sOff[c]; o2 = b2 + sOff[GP + c]; o3 = b3 + sOff[2 * GP + c];
+        o1 = sOff[c]; o2 = sOff[GP + c]; o3 = sOff[2 * GP + c];
     }
+
     // All-gather.  Owner threads publish `v` for their row; the last owner thread also publishes the CTA's block
     // totals (B1,B2,B3).  Every thread collects the rows k = tid*KPT + j, every CTA scans the totals into sOff.
     //   X_USE_OFF: out = v_k - (rho_1[k] off_1 + rho_2[k] off_2 + rho_3[k] off_3) with the offsets of k's owner
@@ -277,7 +282,7 @@ struct Team {
             epoch++;
             double *cur = xbase + (size_t)(epoch & 3u) * P.xbuf_words, *clr = xbase + (size_t)((epoch + 2u) & 3u) * P.xbuf_words;
 #ifdef MCT_PROFILE
-#define SNAP(i) do { if (epoch == 1000u) { long long g__; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g__)); prof[i] = g__; } } while (0)
+#define SNAP(i) do { if (epoch == (unsigned)P.snap_epoch) { long long g__; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g__)); prof[i] = g__; } } while (0)
 #else
 #define SNAP(i) do { } while (0)
 #endif
@@ -337,14 +342,19 @@ struct Team {
             }
             SNAP(21);
             if (tid < 32 * kMaxTotWarps && warp * 32 < P.G) {
-                // exclusive prefix of the totals inside each warp of 32 CTAs, warp totals aside
+                // exclusive prefix of the G block totals in a fixed order: inside each warp of 32 CTAs, then the totals of
+                // the warps before (named barrier 2 among the <= 5 scanning warps)
                 const double b1 = bits2d(t0w), b2 = bits2d(t1w), b3 = bits2d(t2w);
                 double s1 = b1, s2 = b2, s3 = b3;
                 warp_inscan3(s1, s2, s3);
+                if (lane == 31) { sWT[warp] = s1; sWT[8 + warp] = s2; sWT[16 + warp] = s3; }
+                const int nscan = ((P.G + 31) >> 5) * 32;
+                asm volatile("bar.sync 2, %0;" ::"r"(nscan) : "memory");
+                double w1 = 0.0, w2 = 0.0, w3 = 0.0;
+                for (int ww = 0; ww < warp; ww++) { w1 += sWT[ww]; w2 += sWT[8 + ww]; w3 += sWT[16 + ww]; }
                 // (an inclusive scan minus the own value is not bit-identical to an exclusive scan, but it is the
                 //  same numbers in every CTA, which is all that is required)
-                if (tot) { sOff[tid] = s1 - b1; sOff[GP + tid] = s2 - b2; sOff[2 * GP + tid] = s3 - b3; }
-                if (lane == 31) { sWT[warp] = s1; sWT[8 + warp] = s2; sWT[16 + warp] = s3; }
+                if (tot) { sOff[tid] = w1 + (s1 - b1); sOff[GP + tid] = w2 + (s2 - b2); sOff[2 * GP + tid] = w3 + (s3 - b3); }
             }
             __syncthreads();
         }
@@ -357,9 +367,15 @@ struct Team {
             const int k = tid * KPT + j;
             double f = bits2d(w[j]);
             if (k < P.Nk) {
+#ifdef MCT_PROFILE
+                if ((flags & X_USE_OFF) && !(P.dbg & 64)) {
+                    double o1, o2, o3;
+                    if (P.dbg & 32) { o1 = myoff1; o2 = myoff2; o3 = myoff3; } else cta_offsets(owner[j], o1, o2, o3);
+#else
                 if (flags & X_USE_OFF) {
                     double o1, o2, o3;
                     cta_offsets(owner[j], o1, o2, o3);
+#endif
                     f = f - (sRho[k] * o1 + sRho[NkP + k] * o2 + sRho[2 * NkP + k] * o3);
                 }
                 if (flags & X_TRACK) { pred |= (fabs(f - fold[j]) > P.tol) ? 1 : 0; fold[j] = f; }

@@ -49,6 +49,7 @@ struct SolveParams {
     long long spin_limit_cycles;
     SmemOffsets so;             // filled by td_sc_launch
     int dbg;                    // debug switches of profile builds (MCT_DBG)
+    int snap_epoch;             // profile builds: exchange whose timeline is recorded (MCT_SNAP_EPOCH)
     long long *prof;            // [G][16] phase cycle counters of team 0 (only filled when built with -DMCT_PROFILE)
 };
 
