@@ -179,37 +179,30 @@ static int upload_traj(mct_kernel_t h, long nt, const double *Fc) {
 }
 
 // ---- team geometry selection ------------------------------------------------------------------------------
-static long long total_groups_of(int Nk, int sym) {
-    long long g = 0;
-    for (int ik = 1; ik <= Nk; ik++) {
-        const int d = ik - 1;
-        const int t = sym ? (Nk - d) + (ik - 1) / 2 + (ik % 2 == 0 ? 1 : 0) : (Nk - d) * (d > 0 ? 2 : 1) + (ik - 1);
-        g += (t + 31) / 32;
-    }
-    return g;
-}
-
 static int env_int(const char *name, int dflt) {
     const char *v = getenv(name);
     return (v && *v) ? atoi(v) : dflt;
 }
 
-struct Residency { int TR, TS, lane_cap; };
+struct Residency { int UR, US, lane_cap; };
 
-// How the T groups of every warp are kept: TR in registers (a kernel instantiation), TS in shared memory, rest in L2.
+// How the U units of every warp are kept: UR in registers (a kernel instantiation), US in shared memory, rest in L2.
 static Residency choose_residency(const TeamLayout &L, size_t smem_optin) {
     Residency r;
-    const int trmax = std::min(td_sc_max_reg_groups(), env_int("MCT_MAX_REG_GROUPS", td_sc_max_reg_groups()));
-    r.TR = 0;
-    for (int tr : {4, 8, 12}) if (tr <= trmax) { r.TR = tr; if (tr >= L.T) break; }
-    r.lane_cap = std::max(1, L.went_max);               // one scratch column set per (warp,row) entry; <= 10 (choose_geometry)
+    // 24 registers per register-resident unit; the instantiation that finishes 4 rows per thread (Nk > 512) has 28
+    // fewer registers to spare (measured: 2 units there, 4 otherwise, keeps spills out of the kernel)
+    const int ur_default = (L.Nk > 2 * kThreads) ? 2 : td_sc_max_reg_units();
+    const int urmax = std::min(td_sc_max_reg_units(), env_int("MCT_MAX_REG_UNITS", ur_default));
+    r.UR = 0;
+    for (int ur : {2, 3, 4}) if (ur <= urmax) { r.UR = ur; if (ur >= L.U) break; }
+    r.lane_cap = std::max(1, L.went_max);               // one scratch column set per (warp, row block) entry
     SolveParams P{};
-    P.Nk = L.Nk; P.G = L.G; P.rows_max = L.rows_max; P.ent_max = L.ent_max; P.lane_cap = r.lane_cap; P.TS = 0;
-    const int want = std::max(0, L.T - r.TR);
+    P.Nk = L.Nk; P.G = L.G; P.rows_max = L.rows_max; P.ent_max = L.ent_max; P.lane_cap = r.lane_cap; P.US = 0;
+    const int want = std::max(0, L.U - r.UR);
     const size_t fixed = td_sc_smem_bytes(P);
-    const size_t per_group = (size_t)kWarps * 32 * (3 * 8 + 4);
-    const int cap = fixed + 64 < smem_optin ? (int)((smem_optin - fixed - 64) / per_group) : 0;
-    r.TS = std::min(want, cap);
+    const size_t per_unit = (size_t)kWarps * (kUV * 32 * 8 + 4);
+    const int cap = fixed + 64 < smem_optin ? (int)((smem_optin - fixed - 64) / per_unit) : 0;
+    r.US = std::min(std::min(want, cap), 32);           // (the descriptors of the shared-memory units are loaded by one warp)
     return r;
 }
 
@@ -217,17 +210,17 @@ static Residency choose_residency(const TeamLayout &L, size_t smem_optin) {
 static int choose_geometry(mct_kernel_t h, int n_eq, TeamLayout **out, int *nteams_out) {
     const int Nk = h->Nk, sym = h->sym;
     const int n_sm = h->n_sm;
-    const long long groups = total_groups_of(Nk, sym);
+    const long long units = layout_total_units(Nk, sym);
     const int g_cap = std::max(1, std::min(n_sm, Nk / 2));               // at least two rows per CTA
     const int g_min = (Nk + kThreads - 1) / kThreads;                    // one owner thread per row
-    // on-chip capacity of one CTA in groups per warp: registers + what shared memory can hold
-    const int t_chip = td_sc_max_reg_groups() + (int)((h->smem_optin - 48 * 1024 - (size_t)40 * Nk) / ((size_t)kWarps * 32 * 28));
-    int G_fit = (int)std::min<long long>(g_cap, std::max<long long>(g_min, (groups + (long long)kWarps * t_chip - 1) / ((long long)kWarps * t_chip)));
+    // on-chip capacity of one CTA in units per warp: registers + what shared memory can hold
+    const int u_chip = td_sc_max_reg_units() + (int)((h->smem_optin - 56 * 1024 - (size_t)48 * Nk) / ((size_t)kWarps * kUV * 32 * 8));
+    int G_fit = (int)std::min<long long>(g_cap, std::max<long long>(g_min, (units + (long long)kWarps * u_chip - 1) / ((long long)kWarps * u_chip)));
     int G;
     if (n_eq == 1) {
-        // latency: as many CTAs as keep every thread busy with a few terms per iteration
-        const int target = env_int("MCT_TARGET_GROUPS", 4);
-        G = (int)std::min<long long>(g_cap, std::max<long long>(G_fit, (groups + (long long)kWarps * target - 1) / ((long long)kWarps * target)));
+        // latency: as many CTAs as keep every warp busy with a couple of units per iteration
+        const int target = env_int("MCT_TARGET_UNITS", 2);
+        G = (int)std::min<long long>(g_cap, std::max<long long>(G_fit, (units + (long long)kWarps * target - 1) / ((long long)kWarps * target)));
     } else {
         // throughput: the smallest team whose tables stay on chip (the exchange is a per-CTA cost)
         G = G_fit;
@@ -246,11 +239,11 @@ static int choose_geometry(mct_kernel_t h, int n_eq, TeamLayout **out, int *ntea
             if (rc) { delete L; return rc; }
             it = g_geoms.emplace(key, L).first;
         }
-        // a warp reduces at most 10 (warp,row) entries per evaluation; short rows in a small team need a larger team
-        if (it->second->went_max <= 10 || G >= g_cap) break;
+        // the warp scratch holds 12 columns per (warp, row block) entry: short rows in a small team need a larger team
+        if (it->second->went_max <= 6 || G >= g_cap) break;
         G++;
     }
-    MCT_REQUIRE(it->second->went_max <= 10, MCT_UNSUPPORTED, "internal: no team geometry with <= 10 rows per warp");
+    MCT_REQUIRE(it->second->went_max <= 8, MCT_UNSUPPORTED, "internal: no team geometry with <= 8 row blocks per warp");
     const int nteams = std::max(1, std::min(n_eq, n_sm / G));
     *out = it->second;
     *nteams_out = nteams;
@@ -261,7 +254,7 @@ static int ensure_slab(mct_kernel_t h, TeamLayout *L, const double **tab) {
     auto it = h->slabs.find(L);
     if (it != h->slabs.end()) { *tab = it->second; return MCT_OK; }
     double *d = nullptr;
-    MCT_CUDA(cudaMalloc(&d, 3 * (size_t)L->slab_terms * sizeof(double)));
+    MCT_CUDA(cudaMalloc(&d, (size_t)L->slab_doubles() * sizeof(double)));
     int rc;
     if (h->d_V1) rc = layout_fill_from_tables(*L, d, h->d_V1, h->d_V2, h->d_V3, h->stream);
     else rc = layout_fill_from_sk(*L, d, h->d_k, h->d_Ck, h->rho, h->kBT, h->m, h->type == K_TAGGED3D, h->stream);
@@ -331,9 +324,9 @@ static int run_batch(int n, mct_equation_t *eqs, int mode, double tol, long long
     P.Nk = h0->Nk; P.G = L->G; P.N = eqs[0]->opts.N; P.nblocks = eqs[0]->nblocks; P.n_eq = n; P.nteams = nteams;
     P.second_order = eqs[0]->second_order;
     P.dt0 = eqs[0]->opts.dt; P.tol = tol; P.max_iter = max_iter;
-    P.T = L->T; P.TR = res.TR; P.TS = res.TS; P.lane_cap = res.lane_cap;
-    P.rows_max = L->rows_max; P.ent_max = L->ent_max; P.slab_terms = L->slab_terms;
-    P.desc = L->d_desc; P.cta_meta = L->d_cta_meta; P.ent_begin = L->d_ent_begin; P.warp_ent = L->d_warp_ent; P.row_owner = L->d_row_owner;
+    P.U = L->U; P.UR = res.UR; P.US = res.US; P.lane_cap = res.lane_cap;
+    P.rows_max = L->rows_max; P.rb_max = L->rb_max; P.ent_max = L->ent_max;
+    P.udesc = L->d_udesc; P.cta_meta = L->d_cta_meta; P.ent_begin = L->d_ent_begin; P.warp_ent = L->d_warp_ent; P.row_owner = L->d_row_owner;
     P.xbuf_words = L->xbuf_words;
     P.xstride = 4LL * L->xbuf_words + 16;      // four rotating buffers + the arrival counter (own line)
     P.poll_delay = env_int("MCT_POLL_DELAY", 300);
@@ -342,8 +335,8 @@ static int run_batch(int n, mct_equation_t *eqs, int mode, double tol, long long
     P.snap_epoch = env_int("MCT_SNAP_EPOCH", 1000);
     P.spin_limit_cycles = (long long)env_int("MCT_SPIN_LIMIT_MS", 2000) * 2000000LL;
     if (env_int("MCT_VERBOSE", 0))
-        fprintf(stderr, "[mct] Nk=%d sym=%d n_eq=%d: teams=%d x G=%d, T=%d groups/warp (TR=%d regs, TS=%d smem, %d L2), rows/CTA<=%d, smem=%zu B\n",
-                P.Nk, h0->sym, n, nteams, P.G, P.T, P.TR, P.TS, P.T - std::min(P.T, P.TR) - P.TS, P.rows_max, td_sc_smem_bytes(P));
+        fprintf(stderr, "[mct] Nk=%d sym=%d n_eq=%d: teams=%d x G=%d, U=%d units/warp (%d regs, %d smem, %d L2), rows/CTA<=%d, entries/warp<=%d, smem=%zu B\n",
+                P.Nk, h0->sym, n, nteams, P.G, P.U, std::min(P.U, P.UR), P.US, std::max(0, P.U - P.UR - P.US), P.rows_max, L->went_max, td_sc_smem_bytes(P));
 
     // communication scratch: exchange buffers and queue mailboxes (all slots armed with the sentinel = 0xFF bytes),
     // queue, abort flag, equation table
@@ -391,8 +384,8 @@ static int run_batch(int n, mct_equation_t *eqs, int mode, double tol, long long
         static const char *nm[kProfSlots] = {"stream+warp reduce", "barrier", "row sums+prefix", "F_loc", "publish+delay", "collect", "offset scan+barrier",
                                             "apply+or-barrier", "between", "step-local", "=exchange alone", "=eval alone", "=eval+exchange", "-", "x:loads", "x:scan", "x:sync", "x:offsets", "x:or-barrier", "-", "-", "-", "-", "-", "-", "-", "-", "-", "-", "-", "TOTAL cycles", "TOTAL ns"};
         const int ctas[3] = {0, P.G / 2, P.G - 1};
-        fprintf(stderr, "[mct profile] Nk=%d G=%d nteams=%d T=%d TR=%d TS=%d; thread 0 of CTA %d / %d / %d (team 0)\n", P.Nk, P.G, nteams,
-                P.T, P.TR, P.TS, ctas[0], ctas[1], ctas[2]);
+        fprintf(stderr, "[mct profile] Nk=%d G=%d nteams=%d U=%d UR=%d US=%d; thread 0 of CTA %d / %d / %d (team 0)\n", P.Nk, P.G, nteams,
+                P.U, P.UR, P.US, ctas[0], ctas[1], ctas[2]);
         for (int i = 0; i < kProfSlots; i++) {
             if (nm[i][0] == '-') continue;
             fprintf(stderr, "   %-20s", nm[i]);

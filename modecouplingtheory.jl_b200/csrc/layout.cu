@@ -43,163 +43,196 @@ __global__ void raw_tables_kernel(int Nk, const double *k, const double *Ck, dou
     V1[ix] = v1; V2[ix] = v2; V3[ix] = v3;
 }
 
-__device__ __forceinline__ double desc_coef(int d) {
-    const int c = (d >> kDescCoefShift) & 3;
-    return c == 0 ? 1.0 : c == 1 ? 2.0 : c == 2 ? -1.0 : -2.0;
+// The term of (unit, lane, row r): indices (a, b) into V and its coefficient; false if the slot is padding.
+__device__ __forceinline__ bool unit_term(const UnitInfo &u, int Nk, int sym, int lane, int r, int &a, int &b, double &coef) {
+    const int d = u.d0 + r, pos = u.a0 + lane;
+    if (d >= u.dend || d >= Nk) return false;
+    if (u.type == 0) {                       // A[q, q+d] (+ A[q+d, q] merged when symmetric)
+        if (pos >= Nk - d) return false;
+        a = pos; b = pos + d; coef = (sym && d > 0) ? 2.0 : 1.0;
+        return true;
+    }
+    if (u.type == 2) {                       // A[q+d, q]   (non-symmetric tables, d > 0)
+        if (d == 0 || pos >= Nk - d) return false;
+        a = pos + d; b = pos; coef = 1.0;
+        return true;
+    }
+    // antidiagonal of row ik = d+1:  -sum_{iq<ik} A[iq, ik-iq]  ->  0-based (pos, d-1-pos), pos <= d-1
+    const int bb = d - 1 - pos;
+    if (bb < 0) return false;
+    if (sym) {                               // pairs (a,b),(b,a) merged: a < b with -2, a == b with -1
+        if (pos > bb) return false;
+        coef = (pos < bb) ? -2.0 : -1.0;
+    } else coef = -1.0;
+    a = pos; b = bb;
+    return true;
 }
 
-// One thread per slab slot: tab_m[slot] = coef * V_m[a,b]  (0 where the slot is padding).
-__global__ void fill_from_tables_kernel(int Nk, long long slab, const int *desc, const double *V1, const double *V2,
+// One thread per (unit, lane): the 12 table values tab[(unit*12 + r*3 + m)*32 + lane] = coef * V_m[a,b] (0 if padding)
+__global__ void fill_from_tables_kernel(int Nk, int sym, long long n_units, const UnitInfo *uinfo, const double *V1, const double *V2,
                                         const double *V3, double *tab) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= slab) return;
-    const int d = desc[i];
-    double v1 = 0.0, v2 = 0.0, v3 = 0.0;
-    if (d & kDescValid) {
-        const int a = d & kDescIdxMask, b = (d >> kDescIdxBits) & kDescIdxMask;
-        const size_t ix = (size_t)a + (size_t)b * Nk;
-        const double cf = desc_coef(d);
-        v1 = cf * V1[ix]; v2 = cf * V2[ix]; v3 = cf * V3[ix];
+    if (i >= n_units * 32) return;
+    const long long unit = i >> 5; const int lane = (int)(i & 31);
+    const UnitInfo u = uinfo[unit];
+    for (int r = 0; r < kRB; r++) {
+        int a = 0, b = 0; double cf = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+        if (u.type >= 0 && unit_term(u, Nk, sym, lane, r, a, b, cf)) {
+            const size_t ix = (size_t)a + (size_t)b * Nk;
+            v1 = cf * V1[ix]; v2 = cf * V2[ix]; v3 = cf * V3[ix];
+        }
+        double *t = tab + (unit * kUV + r * 3) * 32 + lane;
+        t[0] = v1; t[32] = v2; t[64] = v3;
     }
-    tab[i] = v1; tab[slab + i] = v2; tab[2 * slab + i] = v3;
 }
 
-__global__ void fill_from_sk_kernel(int Nk, long long slab, const int *desc, const double *k, const double *Ck, double rho,
-                                    double D0, double pi2c, double dk, int tagged, double *tab) {
+__global__ void fill_from_sk_kernel(int Nk, int sym, long long n_units, const UnitInfo *uinfo, const double *k, const double *Ck,
+                                    double rho, double D0, double pi2c, double dk, int tagged, double *tab) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= slab) return;
-    const int d = desc[i];
-    double v1 = 0.0, v2 = 0.0, v3 = 0.0;
-    if (d & kDescValid) {
-        const int a = d & kDescIdxMask, b = (d >> kDescIdxBits) & kDescIdxMask;  // A[a,b] = V[a,b] F1[a] F2[b]; q = k[a], p = k[b]
-        if (tagged) vertex_tagged(k[b], k[a], Ck[a], D0, rho, pi2c, dk * dk, v1, v2, v3);
-        else vertex_collective(k[b], k[a], Ck[b], Ck[a], D0, rho, pi2c, dk, v1, v2, v3);
-        const double cf = desc_coef(d);
-        v1 = cf * v1; v2 = cf * v2; v3 = cf * v3;
+    if (i >= n_units * 32) return;
+    const long long unit = i >> 5; const int lane = (int)(i & 31);
+    const UnitInfo u = uinfo[unit];
+    for (int r = 0; r < kRB; r++) {
+        int a = 0, b = 0; double cf = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+        if (u.type >= 0 && unit_term(u, Nk, sym, lane, r, a, b, cf)) {   // A[a,b] = V[a,b] F1[a] F2[b]; q = k[a], p = k[b]
+            if (tagged) vertex_tagged(k[b], k[a], Ck[a], D0, rho, pi2c, dk * dk, v1, v2, v3);
+            else vertex_collective(k[b], k[a], Ck[b], Ck[a], D0, rho, pi2c, dk, v1, v2, v3);
+            v1 = cf * v1; v2 = cf * v2; v3 = cf * v3;
+        }
+        double *t = tab + (unit * kUV + r * 3) * 32 + lane;
+        t[0] = v1; t[32] = v2; t[64] = v3;
     }
-    tab[i] = v1; tab[slab + i] = v2; tab[2 * slab + i] = v3;
 }
 
 namespace {
 
-struct Term { int a, b, coef; };   // coef code: 0:+1 1:+2 2:-1 3:-2
-
-// Terms of the increment of row ik (1-based), in a fixed canonical order.
-void row_terms(int Nk, int ik, int sym, std::vector<Term> &out) {
-    out.clear();
-    const int d = ik - 1;
-    if (sym) {
-        for (int i = 0; i < Nk - d; i++) out.push_back({i, i + d, d > 0 ? 1 : 0});         // A[q,q+d] + A[q+d,q]
-        for (int a = 0; a < (ik - 1) / 2; a++) out.push_back({a, ik - 2 - a, 3});          // -(A[a,b] + A[b,a]), a < b
-        if (ik % 2 == 0) out.push_back({ik / 2 - 1, ik / 2 - 1, 2});                       // -A[a,a]
-    } else {
-        for (int i = 0; i < Nk - d; i++) out.push_back({i, i + d, 0});
-        if (d > 0) for (int i = 0; i < Nk - d; i++) out.push_back({i + d, i, 0});
-        for (int a = 0; a <= ik - 2; a++) out.push_back({a, ik - 2 - a, 2});
-    }
+// units of the row block starting at row d0 (rows d0 .. min(d0+4, dend)-1), appended in a fixed order
+void block_units(int Nk, int sym, int d0, int dend, std::vector<UnitInfo> &out) {
+    const int nd = (Nk - d0 + 31) / 32;                               // longest diagonal run of the block: row d0
+    for (int i = 0; i < nd; i++) out.push_back({0, d0, dend, 32 * i});
+    const int dlast = std::min(d0 + kRB, dend) - 1;
+    if (!sym && dlast > 0) for (int i = 0; i < nd; i++) out.push_back({2, d0, dend, 32 * i});
+    // antidiagonal: positions 0 .. d-1 (non-symmetric) or 0 .. (d-1)/2 (symmetric) for the longest row dlast
+    const int na = sym ? (dlast - 1) / 2 + 1 : dlast;
+    if (dlast >= 1) for (int i = 0; i < (na + 31) / 32; i++) out.push_back({1, d0, dend, 32 * i});
 }
 
-int row_nterms(int Nk, int ik, int sym) {
-    const int d = ik - 1;
-    if (sym) return (Nk - d) + (ik - 1) / 2 + (ik % 2 == 0 ? 1 : 0);
-    return (Nk - d) * (d > 0 ? 2 : 1) + (ik - 1);
+int block_unit_count(int Nk, int sym, int d0, int dend) {
+    const int nd = (Nk - d0 + 31) / 32;
+    const int dlast = std::min(d0 + kRB, dend) - 1;
+    int n = nd;
+    if (!sym && dlast > 0) n += nd;
+    if (dlast >= 1) n += ((sym ? (dlast - 1) / 2 + 1 : dlast) + 31) / 32;
+    return n;
 }
 
-// Contiguous partition of the rows into G ranges minimising the largest number of groups; every range non-empty.
+// Contiguous partition of the rows into G ranges (every range non-empty) minimising the largest unit count.  Row blocks
+// start at the first row of a range, so the cost of a range is evaluated as a whole.
+long long range_units(int Nk, int sym, int r0, int r1) {
+    long long n = 0;
+    for (int d0 = r0; d0 < r1; d0 += kRB) n += block_unit_count(Nk, sym, d0, r1);
+    return n;
+}
+// time a CTA spends on a range: every unit costs its operand loads (~2 row-equivalents) plus one product and three
+// FMAs per row that exists (a trailing block with fewer than 4 rows skips the arithmetic of the missing rows)
+long long range_cost(int Nk, int sym, int r0, int r1) {
+    long long n = 0;
+    for (int d0 = r0; d0 < r1; d0 += kRB) n += (long long)block_unit_count(Nk, sym, d0, r1) * (2 + std::min(kRB, r1 - d0));
+    return n;
+}
+
 void partition_rows(int Nk, int G, int sym, std::vector<int> &row0) {
-    std::vector<int> ng(Nk);
-    long long total = 0;
-    int biggest = 0;
-    for (int r = 0; r < Nk; r++) { ng[r] = (row_nterms(Nk, r + 1, sym) + 31) / 32; total += ng[r]; biggest = std::max(biggest, ng[r]); }
-    auto ranges_needed = [&](long long cap) {
-        int n = 1; long long cur = 0;
-        for (int r = 0; r < Nk; r++) { if (cur + ng[r] > cap) { n++; cur = 0; } cur += ng[r]; }
-        return n;
+    auto fits = [&](long long cap, std::vector<int> *out) {
+        int c = 0, r = 0;
+        if (out) out->assign(G + 1, Nk);
+        while (r < Nk) {
+            if (c >= G) return false;
+            if (out) (*out)[c] = r;
+            // largest end such that the range costs <= cap, leaving at least one row for every later CTA
+            int hi = Nk - (G - 1 - c), e = r + 1;
+            if (range_cost(Nk, sym, r, e) > cap) return false;
+            int lo = e;
+            while (lo < hi) { const int mid = (lo + hi + 1) / 2; if (range_cost(Nk, sym, r, mid) <= cap) lo = mid; else hi = mid - 1; }
+            r = lo; c++;
+        }
+        if (out) for (int i = c; i <= G; i++) (*out)[i] = Nk;
+        return c <= G;
     };
-    long long lo = std::max<long long>(biggest, (total + G - 1) / G), hi = total;
-    while (lo < hi) { const long long mid = (lo + hi) / 2; if (ranges_needed(mid) <= G) hi = mid; else lo = mid + 1; }
-    row0.assign(G + 1, Nk);
-    int c = 0; long long cur = 0;
-    row0[0] = 0;
-    for (int r = 0; r < Nk; r++) {
-        const int rows_left = Nk - r, ctas_after = G - 1 - c;      // rows still to place (with r), CTAs after this one
-        if (cur > 0 && (cur + ng[r] > lo || rows_left <= ctas_after)) { c++; row0[c] = r; cur = 0; }
-        cur += ng[r];
-    }
-    for (int i = c + 1; i <= G; i++) row0[i] = Nk;
+    long long lo = 1, hi = range_cost(Nk, sym, 0, Nk);
+    while (lo < hi) { const long long mid = (lo + hi) / 2; if (fits(mid, nullptr)) hi = mid; else lo = mid + 1; }
+    fits(lo, &row0);
+    // ranges the greedy packing left empty at the end: give them one row each from their predecessor
+    for (int c = G - 1; c >= 1; c--)
+        if (row0[c] >= row0[c + 1]) row0[c] = row0[c + 1] - 1;
 }
 
 }  // namespace
 
-int layout_groups_per_warp(int Nk, int G, int sym, int *rows_max) {
-    std::vector<int> row0;
-    partition_rows(Nk, G, sym, row0);
-    long long gmax = 0; int rmax = 0;
-    for (int c = 0; c < G; c++) {
-        long long g = 0;
-        for (int r = row0[c]; r < row0[c + 1]; r++) g += (row_nterms(Nk, r + 1, sym) + 31) / 32;
-        gmax = std::max(gmax, g); rmax = std::max(rmax, row0[c + 1] - row0[c]);
-    }
-    if (rows_max) *rows_max = rmax;
-    return (int)((gmax + kWarps - 1) / kWarps);
-}
+long long layout_total_units(int Nk, int sym) { return range_units(Nk, sym, 0, Nk); }
 
 int layout_build_geometry(TeamLayout &L, int Nk, int G, int sym) {
-    MCT_REQUIRE(Nk <= (1 << kDescIdxBits), MCT_UNSUPPORTED, "Nk > 2048 is not supported by the persistent solver");
+    MCT_REQUIRE(Nk <= (1 << kUA0Bits), MCT_UNSUPPORTED, "Nk > 2048 is not supported by the persistent solver");
     L.Nk = Nk; L.G = G; L.sym = sym;
     std::vector<int> row0;
     partition_rows(Nk, G, sym, row0);
     for (int c = 0; c < G; c++) MCT_REQUIRE(row0[c + 1] > row0[c], MCT_BAD_ARGUMENT, "team larger than the number of rows");
-    int rows_max = 0;
-    L.T = layout_groups_per_warp(Nk, G, sym, &rows_max);
-    L.rows_max = rows_max;
-    const int T = L.T;
-    const long long cta_slots = (long long)kWarps * T * 32;
-    L.slab_terms = cta_slots * G;
-    std::vector<int> desc((size_t)L.slab_terms, 0), meta(4 * G, 0), ent_begin((size_t)G * (rows_max + 1), 0), warp_ent((size_t)G * (kWarps + 1), 0),
-        owner(Nk, 0);
-    L.ent_max = 1; L.went_max = 1;
-    std::vector<Term> terms;
+    long long umax = 0;
+    L.rows_max = 0; L.rb_max = 0;
     for (int c = 0; c < G; c++) {
-        int *dc = desc.data() + (size_t)c * cta_slots;
-        const int nrows = row0[c + 1] - row0[c];
-        std::vector<int> group_row;     // local row of every group of this CTA
-        for (int lr = 0; lr < nrows; lr++) {
-            const int r = row0[c] + lr;
-            owner[r] = c;
-            row_terms(Nk, r + 1, sym, terms);
-            const int gs = (int)group_row.size(), ngr = ((int)terms.size() + 31) / 32;
-            for (int g = 0; g < ngr; g++) group_row.push_back(lr);
-            for (size_t i = 0; i < terms.size(); i++)
-                dc[(size_t)gs * 32 + i] = terms[i].a | (terms[i].b << kDescIdxBits) | (terms[i].coef << kDescCoefShift) | kDescValid;
+        umax = std::max(umax, range_units(Nk, sym, row0[c], row0[c + 1]));
+        L.rows_max = std::max(L.rows_max, row0[c + 1] - row0[c]);
+        L.rb_max = std::max(L.rb_max, (row0[c + 1] - row0[c] + kRB - 1) / kRB);
+    }
+    const int U = (int)((umax + kWarps - 1) / kWarps);
+    L.U = U;
+    L.n_units = (long long)G * kWarps * U;
+    std::vector<int> udesc((size_t)L.n_units, 0), meta(4 * G, 0), ent_begin((size_t)G * (L.rb_max + 1), 0), warp_ent((size_t)G * (kWarps + 1), 0),
+        owner(Nk, 0);
+    std::vector<UnitInfo> uinfo((size_t)L.n_units, UnitInfo{-1, 0, 0, 0});
+    L.ent_max = 1; L.went_max = 1;
+    for (int c = 0; c < G; c++) {
+        const int r0 = row0[c], r1 = row0[c + 1];
+        for (int r = r0; r < r1; r++) owner[r] = c;
+        std::vector<UnitInfo> units; std::vector<int> unit_rb;
+        for (int d0 = r0, q = 0; d0 < r1; d0 += kRB, q++) {
+            const size_t before = units.size();
+            block_units(Nk, sym, d0, r1, units);
+            for (size_t i = before; i < units.size(); i++) unit_rb.push_back(q);
         }
-        const int GC = (int)group_row.size();
-        MCT_REQUIRE(GC <= kWarps * T, MCT_CUDA_ERROR, "internal: layout overflow");
-        // entries: (warp,row) pairs in group order
-        int n_ent = 0, prev_row = -1;
-        for (int lr = 0; lr <= nrows; lr++) ent_begin[(size_t)c * (rows_max + 1) + lr] = 0;
+        const int nu = (int)units.size();
+        MCT_REQUIRE(nu <= kWarps * U, MCT_CUDA_ERROR, "internal: layout overflow");
+        const int nrb = (r1 - r0 + kRB - 1) / kRB;
+        // deal the units to the warps in order, as evenly as possible
+        int n_ent = 0, prev_rb = -1, next = 0;
+        int *eb = ent_begin.data() + (size_t)c * (L.rb_max + 1);
         for (int w = 0; w < kWarps; w++) {
             warp_ent[(size_t)c * (kWarps + 1) + w] = n_ent;
+            const int cnt = nu / kWarps + (w < nu % kWarps ? 1 : 0);
             int prev = -1, nw = 0;
-            for (int j = 0; j < T; j++) {
-                const int g = w * T + j;
-                if (g >= GC) break;
-                const int lr = group_row[g];
-                if (lr != prev) {
-                    if (prev >= 0) for (int l = 0; l < 32; l++) dc[(size_t)g * 32 + l] |= kDescNewEntry;
-                    if (lr != prev_row) {   // first entry of this row: rows before it (if any were skipped) start here too
-                        for (int q = prev_row + 1; q <= lr; q++) ent_begin[(size_t)c * (rows_max + 1) + q] = n_ent;
-                        prev_row = lr;
-                    }
-                    n_ent++; nw++; prev = lr;
+            for (int j = 0; j < cnt; j++, next++) {
+                const UnitInfo &u = units[next];
+                const int q = unit_rb[next];
+                const size_t slot = ((size_t)c * kWarps + w) * U + j;
+                uinfo[slot] = u;
+                // window start of lane 0 (see layout.cuh), biased so that it is never negative
+                const int w0 = (u.type == 1) ? u.d0 - 1 - u.a0 : u.d0 + u.a0;
+                int d = u.a0 | ((w0 + kFPad) << kUW0Shift) | kUValid | ((std::min(kRB, u.dend - u.d0) - 1) << kURowsShift);
+                if (u.type == 1) d |= kUNeg;
+                if (u.type == 2) d |= kUSwap;
+                if (q != prev) {
+                    if (prev >= 0) d |= kUNewEntry;
+                    if (q != prev_rb) { for (int x = prev_rb + 1; x <= q; x++) eb[x] = n_ent; prev_rb = q; }
+                    n_ent++; nw++; prev = q;
                 }
+                udesc[slot] = d;
             }
             L.went_max = std::max(L.went_max, nw);
         }
         warp_ent[(size_t)c * (kWarps + 1) + kWarps] = n_ent;
-        for (int q = prev_row + 1; q <= rows_max; q++) ent_begin[(size_t)c * (rows_max + 1) + q] = n_ent;
+        for (int x = prev_rb + 1; x <= L.rb_max; x++) eb[x] = n_ent;
+        (void)nrb;
         L.ent_max = std::max(L.ent_max, n_ent);
-        meta[4 * c] = row0[c]; meta[4 * c + 1] = nrows; meta[4 * c + 2] = n_ent;
+        meta[4 * c] = r0; meta[4 * c + 1] = r1 - r0; meta[4 * c + 2] = n_ent;
     }
     L.xbuf_words = 4 * G + ((Nk + 15) / 16) * 16 + 16;
     auto up = [](int **dst, const std::vector<int> &v) {
@@ -207,23 +240,25 @@ int layout_build_geometry(TeamLayout &L, int Nk, int G, int sym) {
         if (e == cudaSuccess) e = cudaMemcpy(*dst, v.data(), v.size() * sizeof(int), cudaMemcpyHostToDevice);
         return e;
     };
-    MCT_CUDA(up(&L.d_desc, desc));
+    MCT_CUDA(up(&L.d_udesc, udesc));
     MCT_CUDA(up(&L.d_cta_meta, meta));
     MCT_CUDA(up(&L.d_ent_begin, ent_begin));
     MCT_CUDA(up(&L.d_warp_ent, warp_ent));
     MCT_CUDA(up(&L.d_row_owner, owner));
+    MCT_CUDA(cudaMalloc(&L.d_uinfo, uinfo.size() * sizeof(UnitInfo)));
+    MCT_CUDA(cudaMemcpy(L.d_uinfo, uinfo.data(), uinfo.size() * sizeof(UnitInfo), cudaMemcpyHostToDevice));
     return MCT_OK;
 }
 
 void layout_free(TeamLayout &L) {
-    cudaFree(L.d_desc); cudaFree(L.d_cta_meta); cudaFree(L.d_ent_begin); cudaFree(L.d_warp_ent); cudaFree(L.d_row_owner);
+    cudaFree(L.d_udesc); cudaFree(L.d_uinfo); cudaFree(L.d_cta_meta); cudaFree(L.d_ent_begin); cudaFree(L.d_warp_ent); cudaFree(L.d_row_owner);
     L = TeamLayout();
 }
 
 int layout_fill_from_tables(const TeamLayout &L, double *d_tab, const double *dV1, const double *dV2, const double *dV3,
                             cudaStream_t s) {
-    const unsigned nb = (unsigned)((L.slab_terms + 255) / 256);
-    fill_from_tables_kernel<<<nb, 256, 0, s>>>(L.Nk, L.slab_terms, L.d_desc, dV1, dV2, dV3, d_tab);
+    const unsigned nb = (unsigned)((L.n_units * 32 + 255) / 256);
+    fill_from_tables_kernel<<<nb, 256, 0, s>>>(L.Nk, L.sym, L.n_units, L.d_uinfo, dV1, dV2, dV3, d_tab);
     count_launch();
     MCT_CUDA(cudaGetLastError());
     return MCT_OK;
@@ -242,8 +277,8 @@ int layout_fill_from_sk(const TeamLayout &L, double *d_tab, const double *dk_arr
     MCT_CUDA(cudaMemcpyAsync(k01, dk_array, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
     MCT_CUDA(cudaStreamSynchronize(s));
     double dk = k01[1] - k01[0];
-    const unsigned nb = (unsigned)((L.slab_terms + 255) / 256);
-    fill_from_sk_kernel<<<nb, 256, 0, s>>>(L.Nk, L.slab_terms, L.d_desc, dk_array, dCk, rho, D0, pi2c, dk, tagged, d_tab);
+    const unsigned nb = (unsigned)((L.n_units * 32 + 255) / 256);
+    fill_from_sk_kernel<<<nb, 256, 0, s>>>(L.Nk, L.sym, L.n_units, L.d_uinfo, dk_array, dCk, rho, D0, pi2c, dk, tagged, d_tab);
     count_launch();
     MCT_CUDA(cudaGetLastError());
     return MCT_OK;

@@ -35,27 +35,29 @@ __host__ __device__ inline int even_up(int n) { return (n + 1) & ~1; }
 
 extern __shared__ __align__(16) unsigned char smem_raw[];
 
-SmemOffsets plan_smem(int Nk, int G, int rows_max, int ent_max, int lane_cap, int TS) {
+SmemOffsets plan_smem(int Nk, int G, int rows_max, int ent_max, int lane_cap, int US) {
     SmemOffsets p;
     size_t o = 0;
-    const int NkP = even_up(Nk);
-    p.F1 = (unsigned)o; o += (size_t)NkP * 8;
-    p.F2 = (unsigned)o; o += (size_t)NkP * 8;
+    const int NkP = even_up(Nk), NkF = even_up(Nk + 2 * kFPad);
+    // F arrays: kFPad zero doubles in front and behind (window operands of padding lanes fall there); the offsets
+    // point at element 0
+    p.F1 = (unsigned)(o + (size_t)kFPad * 8); o += (size_t)NkF * 8;
+    p.F2 = (unsigned)(o + (size_t)kFPad * 8); o += (size_t)NkF * 8;
     p.rho = (unsigned)o; o += (size_t)3 * NkP * 8;
     p.off = (unsigned)o; o += (size_t)3 * even_up(G) * 8;
     p.wt = (unsigned)o; o += (size_t)3 * 8 * 8;                      // totals of the (<= 5) warps that scan the CTA totals
     p.own = (unsigned)o; o += (size_t)kOwnFields * even_up(rows_max) * 8;
-    p.part = (unsigned)o; o += (size_t)3 * even_up(ent_max) * 8;
-    p.lane = (unsigned)o; o += (size_t)kWarps * lane_cap * 3 * kLaneStride * 8;
+    p.part = (unsigned)o; o += (size_t)kUV * even_up(ent_max) * 8;
+    p.lane = (unsigned)o; o += (size_t)kWarps * lane_cap * kUV * kLaneStride * 8;
     p.C = (unsigned)o; o += (size_t)2 * even_up(rows_max) * 8;
     p.X = (unsigned)o; o += (G == 1 ? (size_t)NkP * 8 : 16);
     p.scan = (unsigned)o; o += (size_t)3 * kWarps * 8;
     p.misc = (unsigned)o; o += 32;
     p.eq = (unsigned)o; o += (sizeof(EqDev) + 15) & ~(size_t)15;
     o = (o + 15) & ~(size_t)15;
-    p.desc = (unsigned)o; o += (size_t)kWarps * TS * 32 * 4;
+    p.desc = (unsigned)o; o += (size_t)even_up(kWarps * US) * 4;
     o = (o + 15) & ~(size_t)15;
-    p.tab = (unsigned)o; o += (size_t)3 * kWarps * TS * 32 * 8;
+    p.tab = (unsigned)o; o += (size_t)kWarps * US * kUV * 32 * 8;
     p.total = (unsigned)o;
     return p;
 }
@@ -90,7 +92,7 @@ __device__ __forceinline__ double bits2d(unsigned long long v) { return __longlo
 
 enum { X_USE_OFF = 1, X_TRACK = 2 };
 
-template <int KPT, int TR>
+template <int KPT, int UR>
 struct Team {
     const SolveParams &P;
     // shared memory arrays: constant offsets (parameter bank) into the dynamic segment -- no registers, no 64-bit pointers
@@ -120,9 +122,9 @@ struct Team {
     int we0, we_n;               // first (warp,row) entry of this warp and how many it has
     int eb0, eb1;                // owner thread tid < nrows: entries of its row
     int owner[KPT];              // owner CTA of the rows this thread finishes (k = tid*KPT + j)
-    // register-resident part of the tables: slots (warp*T + j)*32 + lane, j < TR
-    double tab[3][TR > 0 ? TR : 1];
-    int desc[TR > 0 ? TR : 1];
+    // register-resident part of the tables: the 12 values of this lane for the first UR units of the warp
+    double tab[UR > 0 ? UR : 1][kUV];
+    int udesc[UR > 0 ? UR : 1];
     // exchange
     double *xbase, *qbase;
     unsigned epoch, qepoch;
@@ -174,15 +176,31 @@ struct Team {
     }
 
     // ------------------------------------------------------------------------------------------ kernel evaluation
-    // Warp scratch: lane partials of the (<= lane_cap) entries of this warp, column (entry*3+m) padded to 33 doubles.
-    // One term slot: f = F1[a] F2[b]; acc_m += tab_m f.  When the group starts a new entry (warp-uniform flag) the
-    // finished partials are parked in the scratch first -- predicated, no branch, so that groups pipeline.
-    __device__ __forceinline__ void term(int d, double t1, double t2, double t3, double &a1, double &a2, double &a3, double *&sl) {
-        const double f = sF1[d & kDescIdxMask] * sF2[(d >> kDescIdxBits) & kDescIdxMask];
-        const bool ne = (d & kDescNewEntry) != 0;
-        if (ne) { sl[0] = a1; sl[kLaneStride] = a2; sl[2 * kLaneStride] = a3; }
-        sl += ne ? 3 * kLaneStride : 0;
-        a1 = fma(t1, f, ne ? 0.0 : a1); a2 = fma(t2, f, ne ? 0.0 : a2); a3 = fma(t3, f, ne ? 0.0 : a3);
+    // One unit (layout.cuh): 32 positions x 4 rows.  Every lane loads its single operand and the 4 consecutive window
+    // operands, forms the 4 products and feeds 12 FMAs with the 12 table values it owns.  When the unit starts a new
+    // (warp, row block) entry the 12 finished partials are parked in the warp scratch first (warp-uniform, rare).
+    // The operands of the NEXT unit are loaded before the arithmetic of this one (op/nop), otherwise every row waits
+    // for its own shared-memory load.
+    struct Operands { double f1, w[kRB]; };
+    __device__ __forceinline__ void load_operands(int d, Operands &o) const {
+        const double *S = (d & kUSwap) ? (const double *)sF2 : sF1, *W = (d & kUSwap) ? sF1 : (const double *)sF2;
+        o.f1 = S[(d & ((1 << kUA0Bits) - 1)) + lane];
+        const double *wp = W + (((d >> kUW0Shift) & ((1 << kUW0Bits) - 1)) - kFPad) + ((d & kUNeg) ? -lane : lane);
+#pragma unroll
+        for (int r = 0; r < kRB; r++) o.w[r] = wp[r];
+    }
+    __device__ __forceinline__ void unit(int d, const Operands &o, const double (&t)[kUV], double (&acc)[kUV], double *&sl) {
+        if (d & kUNewEntry) {
+#pragma unroll
+            for (int v = 0; v < kUV; v++) { sl[v * kLaneStride] = acc[v]; acc[v] = 0.0; }
+            sl += kUV * kLaneStride;
+        }
+        // rows of the block that do not exist (a trailing block of the CTA's range) are skipped: warp-uniform branches
+        const int nr = (d >> kURowsShift) & 3;
+        { const double f = o.f1 * o.w[0]; acc[0] = fma(t[0], f, acc[0]); acc[1] = fma(t[1], f, acc[1]); acc[2] = fma(t[2], f, acc[2]); }
+        if (nr >= 1) { const double f = o.f1 * o.w[1]; acc[3] = fma(t[3], f, acc[3]); acc[4] = fma(t[4], f, acc[4]); acc[5] = fma(t[5], f, acc[5]); }
+        if (nr >= 2) { const double f = o.f1 * o.w[2]; acc[6] = fma(t[6], f, acc[6]); acc[7] = fma(t[7], f, acc[7]); acc[8] = fma(t[8], f, acc[8]); }
+        if (nr >= 3) { const double f = o.f1 * o.w[3]; acc[9] = fma(t[9], f, acc[9]); acc[10] = fma(t[10], f, acc[10]); acc[11] = fma(t[11], f, acc[11]); }
     }
 
     // evaluate_kernel!(K, kernel, F, t) for the whole team (src/Kernels/ModeCouplingKernels.jl:211-228, 450-467),
@@ -195,41 +213,68 @@ struct Team {
         if (epoch + 1 == (unsigned)P.snap_epoch) { long long g__; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g__)); prof[24] = g__; }
 #endif
         {
-            double a1 = 0.0, a2 = 0.0, a3 = 0.0;
-            double *const sl0 = sLane + (size_t)warp * P.lane_cap * 3 * kLaneStride + lane;
-            double *sl = sl0;
+            double acc[kUV];
 #pragma unroll
-            for (int j = 0; j < TR; j++) {
-                int d = desc[j];
-                asm volatile("" : "+r"(d));       // keep the packed descriptor: unpacked addresses would double the registers
-                term(d, tab[0][j], tab[1][j], tab[2][j], a1, a2, a3, sl);
+            for (int v = 0; v < kUV; v++) acc[v] = 0.0;
+            double *const sl0 = sLane + (size_t)warp * P.lane_cap * kUV * kLaneStride + lane;
+            double *sl = sl0;
+            const int US = P.US;
+            const int UG = P.U - UR - US;           // units that fit neither registers nor shared memory: from L2
+            Operands op, nop;
+            int dn = (UR > 0) ? udesc[0] : (US > 0 ? sDesc[warp * US] : (UG > 0 ? __ldg(P.udesc + slab_base + (long long)warp * P.U) : 0));
+            load_operands(dn, op);
+#ifdef MCT_PROFILE
+            if (!(P.dbg & 256))
+#endif
+#pragma unroll
+            for (int u = 0; u < UR; u++) {
+                const int d = dn;
+                dn = (u + 1 < UR) ? udesc[u + 1] : (US > 0 ? sDesc[warp * US] : (UG > 0 ? __ldg(P.udesc + slab_base + (long long)warp * P.U + UR) : 0));
+                load_operands(dn, nop);
+                unit(d, op, tab[u], acc, sl);
+                op = nop;
             }
-            const int TS = P.TS;
-            if (TS > 0) {
-                const int sts = kWarps * TS * 32;
-                const double *t1 = sTab + (size_t)warp * TS * 32 + lane, *t2 = t1 + sts, *t3 = t2 + sts;
-                const int *dd = sDesc + warp * TS * 32 + lane;
-#pragma unroll 4
-                for (int j = 0; j < TS; j++) term(dd[j * 32], t1[j * 32], t2[j * 32], t3[j * 32], a1, a2, a3, sl);
+#ifdef MCT_PROFILE
+            if (!(P.dbg & 512))
+#endif
+            for (int u = 0; u < US; u++) {
+                double t[kUV];
+                const double *ts = sTab + ((size_t)(warp * US + u) * kUV) * 32 + lane;
+#pragma unroll
+                for (int v = 0; v < kUV; v++) t[v] = ts[v * 32];
+                const int d = dn;
+                dn = (u + 1 < US) ? sDesc[warp * US + u + 1] : (UG > 0 ? __ldg(P.udesc + slab_base + (long long)warp * P.U + UR + US) : 0);
+                load_operands(dn, nop);
+                unit(d, op, t, acc, sl);
+                op = nop;
             }
-            const int TG = P.T - TR - TS;          // groups that fit neither registers nor shared memory: from L2
-            if (TG > 0) {
-                const long long base = slab_base + ((long long)warp * P.T + TR + TS) * 32 + lane;
-                const double *t1 = gtab + base, *t2 = t1 + P.slab_terms, *t3 = t2 + P.slab_terms;
-                const int *dd = P.desc + base;
-#pragma unroll 4
-                for (int j = 0; j < TG; j++) term(__ldg(dd + j * 32), __ldg(t1 + j * 32), __ldg(t2 + j * 32), __ldg(t3 + j * 32), a1, a2, a3, sl);
+            for (int u = 0; u < UG; u++) {
+                const long long slot = slab_base + (long long)warp * P.U + UR + US + u;
+                double t[kUV];
+                const double *ts = gtab + (slot * kUV) * 32 + lane;
+#pragma unroll
+                for (int v = 0; v < kUV; v++) t[v] = __ldg(ts + v * 32);
+                const int d = dn;
+                dn = (u + 1 < UG) ? __ldg(P.udesc + slot + 1) : 0;
+                load_operands(dn, nop);
+                unit(d, op, t, acc, sl);
+                op = nop;
             }
-            // last entry, then lane l < 3*we_n adds the 32 lane partials of column l
-            if (we_n > 0) { sl[0] = a1; sl[kLaneStride] = a2; sl[2 * kLaneStride] = a3; }
+            // last entry, then lanes add the 32 lane partials of the 12*we_n columns
+            if (we_n > 0) {
+#pragma unroll
+                for (int v = 0; v < kUV; v++) sl[v * kLaneStride] = acc[v];
+            }
             __syncwarp();
-            if (lane < 3 * we_n) {
-                const double *col = sl0 - lane + lane * kLaneStride;
+#ifdef MCT_PROFILE
+            if (!(P.dbg & 128))
+#endif
+            for (int c = lane; c < kUV * we_n; c += 32) {
+                const double *col = sl0 - lane + (size_t)c * kLaneStride;
                 double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) { s0 += col[i]; s1 += col[i + 1]; s2 += col[i + 2]; s3 += col[i + 3]; }
-                const int e = lane / 3, m = lane - 3 * e;
-                sPart[m * EP + we0 + e] = (s0 + s1) + (s2 + s3);
+                sPart[we0 * kUV + c] = (s0 + s1) + (s2 + s3);
             }
         }
         PROF(0);
@@ -237,8 +282,10 @@ struct Team {
         PROF(1);
         // increments of the owned rows, inclusive prefix over them
         double i1 = 0.0, i2 = 0.0, i3 = 0.0;
-        if (tid < nrows)
-            for (int e = eb0; e < eb1; e++) { i1 += sPart[e]; i2 += sPart[EP + e]; i3 += sPart[2 * EP + e]; }
+        if (tid < nrows) {
+            const int r3 = 3 * (tid & (kRB - 1));          // row inside its row block
+            for (int e = eb0; e < eb1; e++) { i1 += sPart[e * kUV + r3]; i2 += sPart[e * kUV + r3 + 1]; i3 += sPart[e * kUV + r3 + 2]; }
+        }
         if (P.rows_max <= 32) { if (warp == 0) warp_inscan3(i1, i2, i3); }
         else block_inscan3(i1, i2, i3);
         L1 = i1; L2 = i2; L3 = i3;
@@ -458,20 +505,16 @@ struct Team {
 
     // ------------------------------------------------------------------------------------------ per-equation setup
     __device__ __forceinline__ void load_tables(const EqDev &E) {
-        const int T = P.T;
 #pragma unroll
-        for (int j = 0; j < TR; j++) {
-            const long long s = slab_base + ((long long)warp * T + j) * 32 + lane;
-            const bool ok = j < T;
-            tab[0][j] = ok ? __ldg(E.tab + s) : 0.0;
-            tab[1][j] = ok ? __ldg(E.tab + P.slab_terms + s) : 0.0;
-            tab[2][j] = ok ? __ldg(E.tab + 2 * P.slab_terms + s) : 0.0;
+        for (int u = 0; u < UR; u++) {
+            const long long slot = slab_base + (long long)warp * P.U + u;
+#pragma unroll
+            for (int v = 0; v < kUV; v++) tab[u][v] = (u < P.U) ? __ldg(E.tab + (slot * kUV + v) * 32 + lane) : 0.0;
         }
-        const int TS = P.TS, sts = kWarps * TS * 32;
-        for (int j = 0; j < TS; j++) {
-            const long long s = slab_base + ((long long)warp * T + TR + j) * 32 + lane;
-            const int d = (warp * TS + j) * 32 + lane;
-            sTab[d] = __ldg(E.tab + s); sTab[sts + d] = __ldg(E.tab + P.slab_terms + s); sTab[2 * sts + d] = __ldg(E.tab + 2 * P.slab_terms + s);
+        const int US = P.US;
+        for (int u = 0; u < US; u++) {
+            const long long slot = slab_base + (long long)warp * P.U + UR + u;
+            for (int v = 0; v < kUV; v++) sTab[((size_t)(warp * US + u) * kUV + v) * 32 + lane] = __ldg(E.tab + (slot * kUV + v) * 32 + lane);
         }
     }
     // F1 operand of a tagged kernel (collective F at trajectory index tix); a later barrier publishes it.
@@ -751,9 +794,9 @@ struct Team {
     }
 };
 
-template <int KPT, int TR>
+template <int KPT, int UR>
 __global__ void __launch_bounds__(kThreads, 1) td_sc_kernel(const SolveParams P) {
-    Team<KPT, TR> T(P);
+    Team<KPT, UR> T(P);
     T.tid = threadIdx.x; T.lane = T.tid & 31; T.warp = T.tid >> 5;
     const int team = blockIdx.x / P.G;
     T.cta = blockIdx.x % P.G;
@@ -761,7 +804,7 @@ __global__ void __launch_bounds__(kThreads, 1) td_sc_kernel(const SolveParams P)
     T.xbase = P.xbuf + (size_t)team * P.xstride;
     T.qbase = P.qbox + (size_t)team * 64;
     T.oF1 = P.so.F1;
-    T.slab_base = (long long)T.cta * kWarps * P.T * 32;
+    T.slab_base = (long long)T.cta * kWarps * P.U;          // first unit slot of this CTA
 #ifdef MCT_PROFILE
     for (int i = 0; i < kProfSlots; i++) T.prof[i] = 0;
     T.tlast = clock64();
@@ -774,14 +817,19 @@ __global__ void __launch_bounds__(kThreads, 1) td_sc_kernel(const SolveParams P)
         T.row0 = P.cta_meta[4 * T.cta]; T.nrows = P.cta_meta[4 * T.cta + 1];
         T.we0 = P.warp_ent[T.cta * (kWarps + 1) + T.warp];
         T.we_n = P.warp_ent[T.cta * (kWarps + 1) + T.warp + 1] - T.we0;
-        const int *eb = P.ent_begin + (size_t)T.cta * (P.rows_max + 1);
-        T.eb0 = (T.tid < T.nrows) ? eb[T.tid] : 0;
-        T.eb1 = (T.tid < T.nrows) ? eb[T.tid + 1] : 0;
+        const int *eb = P.ent_begin + (size_t)T.cta * (P.rb_max + 1);
+        T.eb0 = (T.tid < T.nrows) ? eb[T.tid / kRB] : 0;
+        T.eb1 = (T.tid < T.nrows) ? eb[T.tid / kRB + 1] : 0;
 #pragma unroll
         for (int j = 0; j < KPT; j++) { const int k = T.tid * KPT + j; T.owner[j] = (k < P.Nk) ? P.row_owner[k] : 0; }
 #pragma unroll
-        for (int j = 0; j < TR; j++) T.desc[j] = (j < P.T) ? P.desc[T.slab_base + ((long long)T.warp * P.T + j) * 32 + T.lane] : 0;
-        for (int j = 0; j < P.TS; j++) ((int *)(smem_raw + P.so.desc))[(T.warp * P.TS + j) * 32 + T.lane] = P.desc[T.slab_base + ((long long)T.warp * P.T + TR + j) * 32 + T.lane];
+        for (int u = 0; u < UR; u++) T.udesc[u] = (u < P.U) ? P.udesc[T.slab_base + (long long)T.warp * P.U + u] : 0;
+        if (T.lane < P.US) ((int *)(smem_raw + P.so.desc))[T.warp * P.US + T.lane] = P.udesc[T.slab_base + (long long)T.warp * P.U + UR + T.lane];
+        // zero padding around the F arrays (window operands of padding lanes)
+        for (int i = T.tid; i < kFPad; i += kThreads) {
+            double *f1 = (double *)(smem_raw + P.so.F1), *f2 = (double *)(smem_raw + P.so.F2);
+            f1[-1 - i] = 0.0; f2[-1 - i] = 0.0; f1[P.Nk + i] = 0.0; f2[P.Nk + i] = 0.0;
+        }
         for (int i = T.tid; i < 3 * even_up(P.G); i += kThreads) ((double *)(smem_raw + P.so.off))[i] = 0.0;
         if (T.tid < 24) ((double *)(smem_raw + P.so.wt))[T.tid] = 0.0;
         for (int i = T.tid; i < 3 * even_up(P.Nk); i += kThreads) ((double *)(smem_raw + P.so.rho))[i] = 0.0;
@@ -823,21 +871,21 @@ __global__ void __launch_bounds__(kThreads, 1) td_sc_kernel(const SolveParams P)
 #undef RP
 
 template <int KPT>
-void *pick_tr(int TR) {
-    switch (TR) {
+void *pick_tr(int UR) {
+    switch (UR) {
         case 0: return (void *)td_sc_kernel<KPT, 0>;
+        case 2: return (void *)td_sc_kernel<KPT, 2>;
+        case 3: return (void *)td_sc_kernel<KPT, 3>;
         case 4: return (void *)td_sc_kernel<KPT, 4>;
-        case 8: return (void *)td_sc_kernel<KPT, 8>;
-        case 12: return (void *)td_sc_kernel<KPT, 12>;
         default: return nullptr;
     }
 }
 
 }  // namespace
 
-size_t td_sc_smem_bytes(const SolveParams &P) { return plan_smem(P.Nk, P.G, P.rows_max, P.ent_max, P.lane_cap, P.TS).total; }
+size_t td_sc_smem_bytes(const SolveParams &P) { return plan_smem(P.Nk, P.G, P.rows_max, P.ent_max, P.lane_cap, P.US).total; }
 
-int td_sc_max_reg_groups() { return 12; }
+int td_sc_max_reg_units() { return 4; }
 
 int td_sc_launch(const SolveParams &P, cudaStream_t stream) {
     const int KPT = (P.Nk + kThreads - 1) / kThreads;
@@ -846,13 +894,13 @@ int td_sc_launch(const SolveParams &P, cudaStream_t stream) {
     MCT_REQUIRE(P.rows_max <= kThreads, MCT_UNSUPPORTED, "more than 512 rows per CTA: use a larger team");
     const size_t smem = td_sc_smem_bytes(P);
     void *fn = nullptr;
-    if (KPT <= 1) fn = pick_tr<1>(P.TR);
-    else if (KPT <= 2) fn = pick_tr<2>(P.TR);
-    else fn = pick_tr<4>(P.TR);
-    MCT_REQUIRE(fn != nullptr, MCT_BAD_ARGUMENT, "internal: no kernel instantiation for this TR");
+    if (KPT <= 1) fn = pick_tr<1>(P.UR);
+    else if (KPT <= 2) fn = pick_tr<2>(P.UR);
+    else fn = pick_tr<4>(P.UR);
+    MCT_REQUIRE(fn != nullptr, MCT_BAD_ARGUMENT, "internal: no kernel instantiation for this UR");
     MCT_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     SolveParams Pc = P;
-    Pc.so = plan_smem(P.Nk, P.G, P.rows_max, P.ent_max, P.lane_cap, P.TS);
+    Pc.so = plan_smem(P.Nk, P.G, P.rows_max, P.ent_max, P.lane_cap, P.US);
     void *args[] = {(void *)&Pc};
     dim3 grid(P.nteams * P.G), block(kThreads);
     if (P.G > 1) {

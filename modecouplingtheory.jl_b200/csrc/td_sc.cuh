@@ -30,12 +30,11 @@ struct SolveParams {
     double dt0, tol;
     long long max_iter;
     // layout geometry shared by every equation of the launch (layout.cuh)
-    int T;                      // groups per warp
-    int TR;                     // groups per warp resident in registers (selects the kernel instantiation)
-    int TS;                     // groups per warp resident in shared memory; the remaining T-TR-TS stream from L2
-    int rows_max, ent_max, lane_cap;
-    long long slab_terms;
-    const int *desc, *cta_meta, *ent_begin, *warp_ent, *row_owner;
+    int U;                      // units per warp (a unit = 32 positions x 4 rows, layout.cuh)
+    int UR;                     // units per warp resident in registers (selects the kernel instantiation)
+    int US;                     // units per warp resident in shared memory; the remaining U-UR-US stream from L2
+    int rows_max, rb_max, ent_max, lane_cap;
+    const int *udesc, *cta_meta, *ent_begin, *warp_ent, *row_owner;
     // team communication
     double *xbuf;               // [nteams][4][xbuf_words]: rotating exchange buffers of self-validating 8-byte slots
     int xbuf_words;
@@ -55,10 +54,10 @@ struct SolveParams {
 
 constexpr int kProfSlots = 32;
 
-// shared memory needed by a launch with these parameters; TS = 0 gives the fixed part
+// shared memory needed by a launch with these parameters; US = 0 gives the fixed part
 size_t td_sc_smem_bytes(const SolveParams &P);
-// largest TR the kernel is instantiated for
-int td_sc_max_reg_groups();
+// largest UR the kernel is instantiated for
+int td_sc_max_reg_units();
 int td_sc_launch(const SolveParams &P, cudaStream_t stream);
 
 }  // namespace mct
