@@ -127,6 +127,18 @@ MCT_API int mct_equation_destroy(mct_equation_t eq);
  * equations are solved by ONE persistent launch per device; status[i]/kernel_evals[i] are per equation. */
 MCT_API int mct_equation_solve_batch(int n, mct_equation_t *eqs, int *status, long *kernel_evals, float *device_ms);
 
+/* ---- one very large multi-component equation sharded over the GPUs of a node (one process per GPU) ----
+ * Every rank creates the SAME equation on its own device, then:
+ *   prepare(q, rank, world, handle)   allocates this rank's exchange buffer and returns its 64-byte CUDA IPC handle;
+ *   -- the host language all-gathers the world handles (any transport) --
+ *   connect(q, handles[world][64])    maps the peers' buffers;
+ *   mct_equation_solve(q)             on all ranks at the same time: the persistent kernel of rank r evaluates the lines
+ *                                     L = r (mod world) of the vertex sum and stores their sums straight into every
+ *                                     rank's buffer over NVLink (self-validating words, no host round trip, no
+ *                                     collective call); everything else is replicated, so all ranks hold the solution. */
+MCT_API int mct_equation_shard_prepare(mct_equation_t eq, int rank, int world, unsigned char *handle_out /* 64 bytes */);
+MCT_API int mct_equation_shard_connect(mct_equation_t eq, const unsigned char *handles /* [world][64] */);
+
 /* solve_steady_state(gamma, F0, kernel; tolerance, max_iterations)  src/SteadyStateMemoryEquation.jl:59-100.
  * gamma: dof doubles (Diagonal / blocks).  F_out, K_out: dof doubles. */
 MCT_API int mct_steady_state(mct_kernel_t kernel, const double *gamma, const double *F0, double tolerance, long max_iterations,

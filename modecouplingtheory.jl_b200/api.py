@@ -52,7 +52,7 @@ EXPORTS = [
     "mct_last_error", "mct_device_count", "mct_version", "mct_launch_count", "mct_sc3d_create", "mct_sc3d_create_from_sk",
     "mct_sc3d_tagged_create", "mct_sc3d_tagged_create_from_sk", "mct_sc3d_tagged_create_from_equation", "mct_mc3d_create",
     "mct_ddim_create", "mct_kernel_eval", "mct_kernel_eval_many", "mct_kernel_destroy", "mct_td_output_len", "mct_td_solve",
-    "mct_equation_create", "mct_equation_solve", "mct_equation_download", "mct_equation_destroy", "mct_equation_solve_batch",
+    "mct_equation_create", "mct_equation_solve", "mct_equation_download", "mct_equation_destroy", "mct_equation_solve_batch", "mct_equation_shard_prepare", "mct_equation_shard_connect",
     "mct_steady_state",
 ]
 
@@ -452,6 +452,22 @@ def solve_resident(dev_eq):
     ms = C.c_float(0)
     _check(load_library().mct_equation_solve(dev_eq._q, C.byref(evals), C.byref(ms)))
     return evals.value, ms.value
+
+
+def shard_equation(dev_eq, rank, world, all_gather):
+    """Shard a resident multi-component equation over `world` GPUs (one process per GPU).  `all_gather(bytes) -> list of
+    bytes` is the host transport for the 64-byte CUDA IPC handles (e.g. torch.distributed.all_gather_object)."""
+    L = load_library()
+    mine = (C.c_ubyte * 64)()
+    _check(L.mct_equation_shard_prepare(dev_eq._q, rank, world, mine))
+    handles = all_gather(bytes(mine))
+    assert len(handles) == world and all(len(h) == 64 for h in handles)
+    buf = (C.c_ubyte * (64 * world)).from_buffer_copy(b"".join(handles))
+    _check(L.mct_equation_shard_connect(dev_eq._q, buf))
+
+
+def download_solution(dev_eq, solver, dof):
+    return _download(dev_eq, solver, dof, False)
 
 
 def solve_into(equation, solver, t, F, K):

@@ -72,6 +72,9 @@ struct mct_equation_s {
     int ns = 1;
     double *d_gws = nullptr;
     GridParams gp{};
+    // k-sharding over GPUs: this rank's exchange buffer (IPC-exported) and the peers' mappings
+    double *d_xshard = nullptr;
+    void *peer_maps[kMaxShardRanks] = {};
 };
 
 namespace mct {
@@ -457,6 +460,7 @@ static int grid_setup(mct_equation_t q, mct_kernel_t h, int mode, const std::vec
     GridParams &g = q->gp;
     g = GridParams{};
     g.type = (h->type == K_MC3D) ? GK_MC3D : GK_DDIM; g.Nk = Nk; g.ns = ns; g.mode = mode;
+    g.rank = 0; g.world = 1; g.spin_limit_cycles = (long long)env_int("MCT_SHARD_SPIN_LIMIT_MS", 20000) * 2000000LL;
     g.kvec = h->d_k; g.C = h->d_C; g.pref = h->d_pref; g.W = h->d_W;
     double *p = q->d_gws;
     g.alpha = p; g.beta = p + dof; g.gamma = p + 2 * dof; g.delta = p + 3 * dof; g.F0 = p + 4 * dof; g.dF0 = p + 5 * dof; p += 6 * dof;
@@ -761,6 +765,8 @@ int mct_equation_destroy(mct_equation_t q) {
     if (!q) return MCT_OK;
     if (q->kernel) cudaSetDevice(q->kernel->device);
     if (q->d_gws) { cudaFree(q->d_gws); q->d_F = nullptr; }
+    for (int r = 0; r < kMaxShardRanks; r++) if (q->peer_maps[r]) cudaIpcCloseMemHandle(q->peer_maps[r]);
+    cudaFree(q->d_xshard);
     cudaFree(q->d_coef); cudaFree(q->d_ring); cudaFree(q->d_F); cudaFree(q->d_status);
     delete q;
     return MCT_OK;
@@ -839,6 +845,37 @@ int mct_td_solve(mct_kernel_t h, const mct_coeffs *c, const double *F0, const do
     int rc2 = mct_equation_download(q, t_out, F_out, K_out);
     mct_equation_destroy(q);
     return rc ? rc : rc2;
+}
+
+int mct_equation_shard_prepare(mct_equation_t q, int rank, int world, unsigned char *handle_out) {
+    MCT_REQUIRE(q && handle_out, MCT_BAD_ARGUMENT, "NULL argument to mct_equation_shard_prepare");
+    MCT_REQUIRE(q->kernel && q->kernel->type == K_MC3D, MCT_UNSUPPORTED, "k-sharding is implemented for the multi-component kernel");
+    MCT_REQUIRE(world >= 2 && world <= kMaxShardRanks && rank >= 0 && rank < world, MCT_BAD_ARGUMENT, "bad rank / world size (2..8)");
+    MCT_CUDA(cudaSetDevice(q->kernel->device));
+    const size_t xwords = (size_t)3 * q->Nk * 3 * q->ns * q->ns;
+    if (!q->d_xshard) MCT_CUDA(cudaMalloc(&q->d_xshard, 4 * xwords * sizeof(double)));
+    MCT_CUDA(cudaMemset(q->d_xshard, 0xFF, 4 * xwords * sizeof(double)));          // every slot armed with the sentinel
+    cudaIpcMemHandle_t hd;
+    MCT_CUDA(cudaIpcGetMemHandle(&hd, q->d_xshard));
+    static_assert(sizeof(hd) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(handle_out, &hd, 64);
+    q->gp.rank = rank; q->gp.world = world;
+    return MCT_OK;
+}
+
+int mct_equation_shard_connect(mct_equation_t q, const unsigned char *handles) {
+    MCT_REQUIRE(q && handles && q->d_xshard && q->gp.world >= 2, MCT_BAD_ARGUMENT, "call mct_equation_shard_prepare first");
+    MCT_CUDA(cudaSetDevice(q->kernel->device));
+    for (int r = 0; r < q->gp.world; r++) {
+        if (r == q->gp.rank) { q->gp.xpeer[r] = q->d_xshard; continue; }
+        cudaIpcMemHandle_t hd;
+        memcpy(&hd, handles + 64 * r, 64);
+        void *p = nullptr;
+        MCT_CUDA(cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
+        q->peer_maps[r] = p;
+        q->gp.xpeer[r] = (double *)p;
+    }
+    return MCT_OK;
 }
 
 int mct_steady_state(mct_kernel_t h, const double *gamma, const double *F0, double tolerance, long max_iterations,

@@ -66,10 +66,23 @@ __device__ __forceinline__ void blk_solve(int ns, const double *A, const double 
         }
 }
 
+constexpr unsigned long long kSentinel = 0xFFFFFFFFFFFFFFFFull;   // a NaN payload no arithmetic produces
+
+__device__ __forceinline__ void st_relaxed_sys(double *p, double v) {
+    asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_bits(const double *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
 struct Ctx {
     const GridParams &P;
     cg::grid_group grid;
     int nb, dof, gtid, gthreads, lane, gwarp, gwarps;
+    unsigned xepoch = 0;
+    bool failed = false;
     __device__ Ctx(const GridParams &p) : P(p), grid(cg::this_grid()) {
         nb = p.ns * p.ns; dof = p.Nk * nb;
         gtid = blockIdx.x * blockDim.x + threadIdx.x; gthreads = gridDim.x * blockDim.x;
@@ -112,7 +125,13 @@ struct Ctx {
         grid.sync();
         // (2) line sums: lines [0, 2Nk-1) are diagonals ip - iq = L-(Nk-1); [2Nk-1, 3Nk-2) antidiagonals iq + ip = L-(2Nk-1)
         const int nlines = 3 * Nk - 2;
-        for (int L = gwarp; L < nlines; L += gwarps) {
+        const int world = P.world, rank = P.rank;
+        const size_t xwords = (size_t)3 * Nk * 3 * nb;
+        xepoch++;
+        double *lcur = (world > 1) ? P.xpeer[rank] + (size_t)(xepoch & 3u) * xwords : P.Lsum;
+        // this rank's lines: L = rank, rank + world, ...  (line lengths vary smoothly with L, so the interleave balances)
+        for (int Li = gwarp; Li * world + rank < nlines; Li += gwarps) {
+            const int L = Li * world + rank;
             double acc[3][kNB];
             for (int m = 0; m < 3; m++) for (int e = 0; e < nb; e++) acc[m][e] = 0.0;
             const bool diag = L < 2 * Nk - 1;
@@ -135,25 +154,48 @@ struct Ctx {
             for (int m = 0; m < 3; m++)
                 for (int e = 0; e < nb; e++) {
                     const double v = warp_sum(acc[m][e]);
-                    if (lane == 0) P.Lsum[(size_t)L * 3 * nb + m * nb + e] = v;
+                    if (lane == 0) {
+                        const size_t w = (size_t)L * 3 * nb + m * nb + e;
+                        if (world == 1) P.Lsum[w] = v;
+                        else for (int r = 0; r < world; r++) st_relaxed_sys(P.xpeer[r] + (size_t)(xepoch & 3u) * xwords + w, v);
+                    }
                 }
+        }
+        if (world > 1) {
+            // re-arm this rank's own copy of the buffer used two exchanges from now (every peer wrote it two exchanges ago
+            // and will write it again only after it has seen this rank's data of the next exchange)
+            unsigned long long *clr = (unsigned long long *)(P.xpeer[rank] + (size_t)((xepoch + 2u) & 3u) * xwords);
+            for (size_t i = gtid; i < xwords; i += gthreads) clr[i] = kSentinel;
+            __threadfence_system();
         }
         grid.sync();
         // (3) bengtzelius3! as a prefix over the line sums, then K = k T1 + T2/k^3 + T3/k   (:2-43, :215-218)
         if (blockIdx.x == 0 && (int)threadIdx.x < nb) {
             const int e = threadIdx.x;
             double t1 = 0.0, t2 = 0.0, t3 = 0.0;
+            const long long t0 = clock64();
+            // line sums of other ranks arrive through NVLink: every word validates itself (sentinel until stored)
+            auto rd = [&](size_t w) -> double {
+                if (world == 1) return lcur[w];
+                unsigned long long v;
+                unsigned spins = 0;
+                while ((v = ld_relaxed_sys_bits(lcur + w)) == kSentinel) {
+                    if ((++spins & 1023u) == 0 && clock64() - t0 > P.spin_limit_cycles) { failed = true; return 0.0; }
+                }
+                return __longlong_as_double((long long)v);
+            };
             for (int ik = 1; ik <= Nk; ik++) {
                 const size_t up = (size_t)((Nk - 1) + (ik - 1)) * 3 * nb, lo = (size_t)((Nk - 1) - (ik - 1)) * 3 * nb;
-                t1 += P.Lsum[up + e]; t2 += P.Lsum[up + nb + e]; t3 += P.Lsum[up + 2 * nb + e];
+                t1 += rd(up + e); t2 += rd(up + nb + e); t3 += rd(up + 2 * nb + e);
                 if (ik > 1) {
-                    t1 += P.Lsum[lo + e]; t2 += P.Lsum[lo + nb + e]; t3 += P.Lsum[lo + 2 * nb + e];
+                    t1 += rd(lo + e); t2 += rd(lo + nb + e); t3 += rd(lo + 2 * nb + e);
                     const size_t an = (size_t)((2 * Nk - 1) + (ik - 2)) * 3 * nb;
-                    t1 -= P.Lsum[an + e]; t2 -= P.Lsum[an + nb + e]; t3 -= P.Lsum[an + 2 * nb + e];
+                    t1 -= rd(an + e); t2 -= rd(an + nb + e); t3 -= rd(an + 2 * nb + e);
                 }
                 const double k = P.kvec[ik - 1];
                 Kout[(size_t)(ik - 1) * nb + e] = k * t1 + t2 / (k * k * k) + t3 / k;
             }
+            if (failed) *P.status = MCT_CUDA_ERROR;
         }
         grid.sync();
     }
@@ -227,7 +269,7 @@ struct Ctx {
                 if (!(err > P.tol)) break;
             }
             for (int e = gtid; e < dof; e += gthreads) { P.F_out[e] = P.Fcur[e]; P.K_out[e] = P.Kcur[e]; }
-            if (gtid == 0) { *P.status = status; *P.kernel_evals = iter; }
+            if (gtid == 0) { if (*P.status != MCT_CUDA_ERROR) *P.status = status; *P.kernel_evals = iter; }
             return;
         }
         // ---- time doubling.  F_old = K0*F0 (:64); K_temp slots keep 2 K0 until they are evaluated (:83)
@@ -365,7 +407,7 @@ struct Ctx {
             }
             grid.sync();
         }
-        if (gtid == 0) { *P.status = status; *P.kernel_evals = evals; }
+        if (gtid == 0) { if (*P.status != MCT_CUDA_ERROR) *P.status = status; *P.kernel_evals = evals; }
 #undef FT
 #undef KT
 #undef FINT

@@ -6,6 +6,7 @@
 namespace mct {
 
 constexpr int kNsMax = 4;
+constexpr int kMaxShardRanks = 8;
 
 enum GridKernelType { GK_MC3D = 3, GK_DDIM = 5 };
 
@@ -28,6 +29,12 @@ struct GridParams {
     unsigned long long *err;     // [2] rotating max-error words (bits of a non-negative double)
     double *F_out, *K_out;       // trajectory [nt][dof]  (mode 1/2: [dof])
     const double *Fin;           // mode 2: input F
+    // k-sharding over GPUs (one process per GPU): rank r computes the line sums of lines L with L % world == r and stores
+    // them straight into every rank's exchange buffer (peer memory over NVLink, IPC-mapped); 4 rotating buffers of
+    // self-validating words, each rank re-arms its own copy.  world == 1: single GPU, Lsum only.
+    int rank, world;
+    double *xpeer[8];            // [world] exchange buffers [4][3*Nk*3*nb] of every rank (own included)
+    long long spin_limit_cycles;
     int *status;
     long long *kernel_evals;
 };
