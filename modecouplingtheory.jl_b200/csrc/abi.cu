@@ -453,7 +453,7 @@ static int grid_setup(mct_equation_t q, mct_kernel_t h, int mode, const std::vec
     const size_t traj = (mode == 0) ? (size_t)q->nt * dof : dof;
     const size_t lsum = (size_t)3 * Nk * 3 * nb;
     const size_t dfh = (mode == 0) ? (size_t)(2 * N + 1) * dof : 0;
-    const size_t total = 6 * dof + 4 * ring + 7 * dof + 3 * dof + lsum + dfh + 2 * traj + 16;
+    const size_t total = 6 * dof + 4 * ring + 7 * dof + 4 * dof + 6 * dof + lsum + dfh + 2 * traj + 16;
     MCT_CUDA(cudaMalloc(&q->d_gws, total * sizeof(double)));
     MCT_CUDA(cudaMemset(q->d_gws, 0, total * sizeof(double)));
     MCT_CUDA(cudaMemcpy(q->d_gws, coef_host.data(), 6 * dof * sizeof(double), cudaMemcpyHostToDevice));
@@ -466,7 +466,8 @@ static int grid_setup(mct_equation_t q, mct_kernel_t h, int mode, const std::vec
     g.alpha = p; g.beta = p + dof; g.gamma = p + 2 * dof; g.delta = p + 3 * dof; g.F0 = p + 4 * dof; g.dF0 = p + 5 * dof; p += 6 * dof;
     g.Ft = p; g.Kt = p + ring; g.FI = p + 2 * ring; g.KI = p + 3 * ring; p += 4 * ring;
     g.C1 = p; g.C2 = p + dof; g.C3 = p + 2 * dof; g.Fold = p + 3 * dof; g.K0 = p + 4 * dof; g.Fcur = p + 5 * dof; g.Kcur = p + 6 * dof; p += 7 * dof;
-    g.G = p; p += 3 * dof;
+    g.G = p; p += 4 * dof;
+    g.Inc = p; p += 3 * dof; g.Tm = p; p += 3 * dof;
     g.Lsum = p; p += lsum;
     g.dFh = p; p += dfh;
     g.F_out = p; g.K_out = p + traj; p += 2 * traj;

@@ -89,6 +89,51 @@ struct Ctx {
         lane = threadIdx.x & 31; gwarp = gtid >> 5; gwarps = gthreads >> 5;
     }
 
+    // line sums of this rank's lines (L = rank, rank + world, ...; line lengths vary smoothly with L, so the interleave
+    // balances); NS is a template parameter so that the 3*NS*NS accumulators live in registers
+    template <int NS>
+    __device__ void line_sums(const double *Fs, const double *G1, const double *G2, const double *G3, int nlines, size_t xwords) {
+        constexpr int NB = NS * NS;
+        const int Nk = P.Nk, world = P.world, rank = P.rank;
+        double pab[NB];
+#pragma unroll
+        for (int e = 0; e < NB; e++) pab[e] = P.pref[e];
+        for (int Li = gwarp; Li * world + rank < nlines; Li += gwarps) {
+            const int L = Li * world + rank;
+            double acc[3][NB];
+#pragma unroll
+            for (int e = 0; e < NB; e++) { acc[0][e] = 0.0; acc[1][e] = 0.0; acc[2][e] = 0.0; }
+            const bool diag = L < 2 * Nk - 1;
+            const int d = L - (Nk - 1), s = L - (2 * Nk - 1);
+            const int q0 = diag ? max(0, -d) : 0, q1 = diag ? min(Nk, Nk - d) : s + 1;
+            for (int iq = q0 + lane; iq < q1; iq += 32) {
+                const int ip = diag ? iq + d : s - iq;
+                const double q = P.kvec[iq], p = P.kvec[ip];
+                const double pq2 = p * p - q * q;
+                const double P1 = p * q, P2 = p * q * (pq2 * pq2), P3 = 2.0 * p * q * pq2;
+#pragma unroll
+                for (int e = 0; e < NB; e++) {
+                    const size_t oq = (size_t)e * Nk + iq, op = (size_t)e * Nk + ip;
+                    const double t1 = Fs[oq] * G1[op], t2 = G2[op] * G3[oq], t3 = G2[oq] * G3[op], t4 = G1[oq] * Fs[op];
+                    acc[0][e] += (t1 + t2 + t3 + t4) * P1 * pab[e];      // :186-192
+                    acc[1][e] += (t1 - t2 - t3 + t4) * P2 * pab[e];
+                    acc[2][e] += (t1 - t4) * P3 * pab[e];
+                }
+            }
+#pragma unroll
+            for (int m = 0; m < 3; m++)
+#pragma unroll
+                for (int e = 0; e < NB; e++) {
+                    const double v = warp_sum(acc[m][e]);
+                    if (lane == 0) {
+                        const size_t w = (size_t)L * 3 * NB + m * NB + e;
+                        if (world == 1) P.Lsum[w] = v;
+                        else for (int r = 0; r < world; r++) st_relaxed_sys(P.xpeer[r] + (size_t)(xepoch & 3u) * xwords + w, v);
+                    }
+                }
+        }
+    }
+
     // ---- K = kernel(F)  (ends with a grid barrier; Kout valid for every thread afterwards)
     __device__ void eval(const double *F, double *Kout) {
         const int Nk = P.Nk, ns = P.ns;
@@ -111,16 +156,19 @@ struct Ctx {
             grid.sync();
             return;
         }
-        // (1) G1 = C'FC, G2 = C'F, G3 = FC per wavenumber
-        double *G1 = P.G, *G2 = P.G + dof, *G3 = P.G + 2 * (size_t)dof;
+        // (1) G1 = C'FC, G2 = C'F, G3 = FC per wavenumber, stored species-major ([e][k]) together with a copy of F so that
+        //     the line walk below reads unit-stride along k
+        double *Fs = P.G, *G1 = P.G + dof, *G2 = P.G + 2 * (size_t)dof, *G3 = P.G + 3 * (size_t)dof;
         for (int k = gtid; k < Nk; k += gthreads) {
             const double *Ck = P.C + (size_t)k * nb, *Fk = F + (size_t)k * nb;
-            double ct[kNB], g3[kNB];
+            double ct[kNB], g1[kNB], g2[kNB], g3[kNB];
             for (int a = 0; a < ns; a++) for (int b = 0; b < ns; b++) ct[a + b * ns] = Ck[b + a * ns];
             blk_mul(ns, Fk, Ck, g3);
-            blk_mul(ns, ct, Fk, G2 + (size_t)k * nb);
-            blk_mul(ns, ct, g3, G1 + (size_t)k * nb);
-            for (int e = 0; e < nb; e++) G3[(size_t)k * nb + e] = g3[e];
+            blk_mul(ns, ct, Fk, g2);
+            blk_mul(ns, ct, g3, g1);
+            for (int e = 0; e < nb; e++) {
+                Fs[(size_t)e * Nk + k] = Fk[e]; G1[(size_t)e * Nk + k] = g1[e]; G2[(size_t)e * Nk + k] = g2[e]; G3[(size_t)e * Nk + k] = g3[e];
+            }
         }
         grid.sync();
         // (2) line sums: lines [0, 2Nk-1) are diagonals ip - iq = L-(Nk-1); [2Nk-1, 3Nk-2) antidiagonals iq + ip = L-(2Nk-1)
@@ -130,36 +178,11 @@ struct Ctx {
         xepoch++;
         double *lcur = (world > 1) ? P.xpeer[rank] + (size_t)(xepoch & 3u) * xwords : P.Lsum;
         // this rank's lines: L = rank, rank + world, ...  (line lengths vary smoothly with L, so the interleave balances)
-        for (int Li = gwarp; Li * world + rank < nlines; Li += gwarps) {
-            const int L = Li * world + rank;
-            double acc[3][kNB];
-            for (int m = 0; m < 3; m++) for (int e = 0; e < nb; e++) acc[m][e] = 0.0;
-            const bool diag = L < 2 * Nk - 1;
-            const int d = L - (Nk - 1), s = L - (2 * Nk - 1);
-            const int q0 = diag ? max(0, -d) : 0, q1 = diag ? min(Nk, Nk - d) : s + 1;
-            for (int iq = q0 + lane; iq < q1; iq += 32) {
-                const int ip = diag ? iq + d : s - iq;
-                const double q = P.kvec[iq], p = P.kvec[ip];
-                const double pq2 = p * p - q * q;
-                const double P1 = p * q, P2 = p * q * (pq2 * pq2), P3 = 2.0 * p * q * pq2;
-                const size_t oq = (size_t)iq * nb, op = (size_t)ip * nb;
-                for (int e = 0; e < nb; e++) {
-                    const double t1 = F[oq + e] * G1[op + e], t2 = G2[op + e] * G3[oq + e], t3 = G2[oq + e] * G3[op + e], t4 = G1[oq + e] * F[op + e];
-                    const double pab = P.pref[e];
-                    acc[0][e] += (t1 + t2 + t3 + t4) * P1 * pab;      // :186-192
-                    acc[1][e] += (t1 - t2 - t3 + t4) * P2 * pab;
-                    acc[2][e] += (t1 - t4) * P3 * pab;
-                }
-            }
-            for (int m = 0; m < 3; m++)
-                for (int e = 0; e < nb; e++) {
-                    const double v = warp_sum(acc[m][e]);
-                    if (lane == 0) {
-                        const size_t w = (size_t)L * 3 * nb + m * nb + e;
-                        if (world == 1) P.Lsum[w] = v;
-                        else for (int r = 0; r < world; r++) st_relaxed_sys(P.xpeer[r] + (size_t)(xepoch & 3u) * xwords + w, v);
-                    }
-                }
+        switch (ns) {
+            case 1: line_sums<1>(Fs, G1, G2, G3, nlines, xwords); break;
+            case 2: line_sums<2>(Fs, G1, G2, G3, nlines, xwords); break;
+            case 3: line_sums<3>(Fs, G1, G2, G3, nlines, xwords); break;
+            default: line_sums<4>(Fs, G1, G2, G3, nlines, xwords); break;
         }
         if (world > 1) {
             // re-arm this rank's own copy of the buffer used two exchanges from now (every peer wrote it two exchanges ago
@@ -169,10 +192,9 @@ struct Ctx {
             __threadfence_system();
         }
         grid.sync();
-        // (3) bengtzelius3! as a prefix over the line sums, then K = k T1 + T2/k^3 + T3/k   (:2-43, :215-218)
-        if (blockIdx.x == 0 && (int)threadIdx.x < nb) {
-            const int e = threadIdx.x;
-            double t1 = 0.0, t2 = 0.0, t3 = 0.0;
+        // (3) bengtzelius3! (:2-43) as a prefix over the line sums: increments per ik (whole grid), then one warp per
+        //     (m, e) sequence scans its Nk increments 32 at a time; K = k T1 + T2/k^3 + T3/k   (:215-218)
+        {
             const long long t0 = clock64();
             // line sums of other ranks arrive through NVLink: every word validates itself (sentinel until stored)
             auto rd = [&](size_t w) -> double {
@@ -184,18 +206,36 @@ struct Ctx {
                 }
                 return __longlong_as_double((long long)v);
             };
-            for (int ik = 1; ik <= Nk; ik++) {
-                const size_t up = (size_t)((Nk - 1) + (ik - 1)) * 3 * nb, lo = (size_t)((Nk - 1) - (ik - 1)) * 3 * nb;
-                t1 += rd(up + e); t2 += rd(up + nb + e); t3 += rd(up + 2 * nb + e);
-                if (ik > 1) {
-                    t1 += rd(lo + e); t2 += rd(lo + nb + e); t3 += rd(lo + 2 * nb + e);
-                    const size_t an = (size_t)((2 * Nk - 1) + (ik - 2)) * 3 * nb;
-                    t1 -= rd(an + e); t2 -= rd(an + nb + e); t3 -= rd(an + 2 * nb + e);
-                }
-                const double k = P.kvec[ik - 1];
-                Kout[(size_t)(ik - 1) * nb + e] = k * t1 + t2 / (k * k * k) + t3 / k;
+            const int nseq = 3 * nb;
+            double *inc = P.Inc;                                   // [nseq][Nk]
+            for (size_t i = gtid; i < (size_t)nseq * Nk; i += gthreads) {
+                const int ik = (int)(i / nseq) + 1, c = (int)(i % nseq);      // consecutive threads: consecutive words of a line
+                double v = rd((size_t)((Nk - 1) + (ik - 1)) * nseq + c);
+                if (ik > 1) { v += rd((size_t)((Nk - 1) - (ik - 1)) * nseq + c); v -= rd((size_t)((2 * Nk - 1) + (ik - 2)) * nseq + c); }
+                inc[(size_t)c * Nk + (ik - 1)] = v;
             }
             if (failed) *P.status = MCT_CUDA_ERROR;
+        }
+        grid.sync();
+        for (int c = gwarp; c < 3 * nb; c += gwarps) {
+            const double *inc = P.Inc + (size_t)c * Nk;
+            double *Tm = P.Tm + (size_t)c * Nk;
+            double carry = 0.0;
+            for (int b0 = 0; b0 < Nk; b0 += 32) {
+                const int ik = b0 + lane;
+                double v = (ik < Nk) ? inc[ik] : 0.0;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const double u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
+                v += carry;
+                if (ik < Nk) Tm[ik] = v;
+                carry = __shfl_sync(0xffffffffu, v, 31);
+            }
+        }
+        grid.sync();
+        for (size_t i = gtid; i < (size_t)dof; i += gthreads) {
+            const int ik = (int)(i / nb), e = (int)(i % nb);
+            const double k = P.kvec[ik];
+            Kout[i] = k * P.Tm[(size_t)e * Nk + ik] + P.Tm[(size_t)(nb + e) * Nk + ik] / (k * k * k) + P.Tm[(size_t)(2 * nb + e) * Nk + ik] / k;
         }
         grid.sync();
     }

@@ -23,7 +23,8 @@ struct GridParams {
     // workspace
     double *Ft, *Kt, *FI, *KI;   // rings [4N][dof]  (slot s at index s-1)
     double *C1, *C2, *C3, *Fold, *K0, *Fcur, *Kcur;   // [dof]
-    double *G;                   // MC: G1, G2, G3 [3][Nk][nb]
+    double *G;                   // MC: F, G1, G2, G3 species-major [4][nb][Nk]
+    double *Inc, *Tm;            // MC: increments and prefix sums [3*nb][Nk]
     double *Lsum;                // line sums [3*Nk][3*nb]
     double *dFh;                 // bootstrap: dF history [2N+1][dof]
     unsigned long long *err;     // [2] rotating max-error words (bits of a non-negative double)
