@@ -194,10 +194,9 @@ static Residency choose_residency(const TeamLayout &L, size_t smem_optin) {
     Residency r;
     // 24 registers per register-resident unit; the instantiation that finishes 4 rows per thread (Nk > 512) has 28
     // fewer registers to spare (measured: 2 units there, 4 otherwise, keeps spills out of the kernel)
-    const int ur_default = (L.Nk > 2 * kThreads) ? 2 : td_sc_max_reg_units();
-    const int urmax = std::min(td_sc_max_reg_units(), env_int("MCT_MAX_REG_UNITS", ur_default));
+    const int urmax = std::min(td_sc_max_reg_units(L.Nk), env_int("MCT_MAX_REG_UNITS", td_sc_max_reg_units(L.Nk)));
     r.UR = 0;
-    for (int ur : {2, 3, 4}) if (ur <= urmax) { r.UR = ur; if (ur >= L.U) break; }
+    for (int ur : {2, 4}) if (ur <= urmax) { r.UR = ur; if (ur >= L.U) break; }
     r.lane_cap = std::max(1, L.went_max);               // one scratch column set per (warp, row block) entry
     SolveParams P{};
     P.Nk = L.Nk; P.G = L.G; P.rows_max = L.rows_max; P.ent_max = L.ent_max; P.lane_cap = r.lane_cap; P.US = 0;
@@ -217,7 +216,7 @@ static int choose_geometry(mct_kernel_t h, int n_eq, TeamLayout **out, int *ntea
     const int g_cap = std::max(1, std::min(n_sm, Nk / 2));               // at least two rows per CTA
     const int g_min = (Nk + kThreads - 1) / kThreads;                    // one owner thread per row
     // on-chip capacity of one CTA in units per warp: registers + what shared memory can hold
-    const int u_chip = td_sc_max_reg_units() + (int)((h->smem_optin - 56 * 1024 - (size_t)48 * Nk) / ((size_t)kWarps * kUV * 32 * 8));
+    const int u_chip = td_sc_max_reg_units(Nk) + (int)((h->smem_optin - 56 * 1024 - (size_t)48 * Nk) / ((size_t)kWarps * kUV * 32 * 8));
     int G_fit = (int)std::min<long long>(g_cap, std::max<long long>(g_min, (units + (long long)kWarps * u_chip - 1) / ((long long)kWarps * u_chip)));
     int G;
     if (n_eq == 1) {

@@ -118,7 +118,8 @@ int sc3d_eval_launch(int Nk, int n, const double *dk, const double *dV1, const d
     sc3d_line_partials<<<grid, 32 * kLineWarps, 0, s>>>(Nk, nseg, dV1, dV2, dV3, dF1, dF2, f1_stride, d_scratch);
     if (KPT <= 1) sc3d_finalize<1><<<n, kThreads, 0, s>>>(Nk, nseg, dk, d_scratch, d_out);
     else if (KPT <= 2) sc3d_finalize<2><<<n, kThreads, 0, s>>>(Nk, nseg, dk, d_scratch, d_out);
-    else sc3d_finalize<4><<<n, kThreads, 0, s>>>(Nk, nseg, dk, d_scratch, d_out);
+    else if (KPT <= 4) sc3d_finalize<4><<<n, kThreads, 0, s>>>(Nk, nseg, dk, d_scratch, d_out);
+    else sc3d_finalize<8><<<n, kThreads, 0, s>>>(Nk, nseg, dk, d_scratch, d_out);
     count_launch(2);
     MCT_CUDA(cudaGetLastError());
     return MCT_OK;

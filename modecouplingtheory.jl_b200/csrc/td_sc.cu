@@ -1,41 +1,16 @@
-// td_sc.cu -- ONE persistent cooperative launch runs the whole Fuchs time-doubling solve
-// (src/TimeDoublingSolver.jl:512-532) of one or many single-component memory equations.
-//
-// A "team" of G CTAs (one CTA per SM) owns one equation at a time (layout.cuh):
-//   * the vertex tables stay resident on chip for the whole solve: every thread keeps the table values of its first
-//     TR term slots in REGISTERS, the next TS in shared memory; only what does not fit streams from L2;
-//   * rows (wavenumbers) are owned by CTAs in contiguous ranges.  Everything local in k -- the memory convolution C3
-//     (:243-288), history rings, time mapping (:448-489) -- is done by the owner and never crosses CTAs;
-//   * one fixed-point iteration (update_K!/update_F!/find_error, :404-417) costs ONE all-gather.  The update is
-//     linear in the Bengtzelius prefix sums:  F[k] = c3/c1 - sum_m rho_m[k] T_m[k],  rho_m = (c2/c1) {k, 1/k^3, 1/k},
-//     and T_m[k] = off_m(owner) + L_m[k] (offset of the owning CTA + prefix inside it).  The owner publishes
-//     F_loc[k] = c3/c1 - sum_m rho_m L_m[k] and its three block totals; every CTA collects all of it, scans the G
-//     totals into offsets and finishes F[k] = F_loc[k] - sum_m rho_m off_m with identical arithmetic, so all CTAs
-//     hold bit-identical iterates and take the same branch with no second exchange.  K itself is only formed
-//     (with the reference's expression k T1 + T2/k^3 + T3/k, :224-227) by the owner when a time step is stored.
-// The all-gather needs no barrier and no fence: every 8-byte slot validates itself.  Slots hold a sentinel bit
-// pattern until their owner stores the value; a reader issues all its loads at once after a short delay and
-// re-issues only those that still show the sentinel.  Four buffers rotate; at exchange e a CTA re-arms its own
-// slots of buffer (e+2)&3, which every CTA finished reading before this CTA could complete exchange e-1
-// ("exchange protocol").  The file is compiled with -fmad=false: FMAs only where fma() is written.
+// td_sc.cu -- host side of the persistent time-doubling solver: shared-memory plan, kernel selection, launch.
+// The kernel itself is in td_sc_impl.cuh, instantiated per wavenumbers-per-thread in td_sc_k{1,2,4,8}.cu.
 #include <algorithm>
 
 #include "td_sc.cuh"
 
 namespace mct {
 
-namespace {
-
-constexpr unsigned long long kSentinel = 0xFFFFFFFFFFFFFFFFull;   // a NaN payload no arithmetic produces
-constexpr int kLaneStride = 33;                                    // padded lane column of the warp scratch
-constexpr int kMaxTotWarps = 5;                                    // warps that scan the CTA totals -> G <= 160
-enum { OWN_K = 0, OWN_F0, OWN_AL, OWN_BE, OWN_GA, OWN_DE, OWN_K0, kOwnFields };   // per-row constants of the owner, in shared memory
-
-__host__ __device__ inline int even_up(int n) { return (n + 1) & ~1; }
-
-extern __shared__ __align__(16) unsigned char smem_raw[];
-
-SmemOffsets plan_smem(int Nk, int G, int rows_max, int ent_max, int lane_cap, int US) {
+void *td_sc_entry_k1(int UR);
+void *td_sc_entry_k2(int UR);
+void *td_sc_entry_k4(int UR);
+void *td_sc_entry_k8(int UR);
+SmemOffsets td_sc_plan_smem(int Nk, int G, int rows_max, int ent_max, int lane_cap, int US) {
     SmemOffsets p;
     size_t o = 0;
     const int NkP = even_up(Nk), NkF = even_up(Nk + 2 * kFPad);
@@ -62,845 +37,26 @@ SmemOffsets plan_smem(int Nk, int G, int rows_max, int ent_max, int lane_cap, in
     return p;
 }
 
-__device__ __forceinline__ void st_relaxed(double *p, double v) {
-    asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
-}
-__device__ __forceinline__ void st_relaxed2(double *p, double a, double b) {
-    asm volatile("st.relaxed.gpu.global.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(a), "d"(b) : "memory");
-}
-__device__ __forceinline__ void st_relaxed_bits(double *p, unsigned long long v) {
-    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ void st_relaxed2_bits(double *p, unsigned long long a, unsigned long long b) {
-    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1,%2};" ::"l"(p), "l"(a), "l"(b) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_relaxed_bits(const double *p) {
-    unsigned long long v;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void ld_relaxed2_bits(const double *p, unsigned long long &a, unsigned long long &b) {
-    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
-}
-__device__ __forceinline__ double bits2d(unsigned long long v) { return __longlong_as_double((long long)v); }
 
-#ifdef MCT_PROFILE
-#define PROF(i) do { long long now__ = clock64(); prof[i] += now__ - tlast; tlast = now__; } while (0)
-#else
-#define PROF(i) do { } while (0)
-#endif
+size_t td_sc_smem_bytes(const SolveParams &P) { return td_sc_plan_smem(P.Nk, P.G, P.rows_max, P.ent_max, P.lane_cap, P.US).total; }
 
-enum { X_USE_OFF = 1, X_TRACK = 2 };
-
-template <int KPT, int UR>
-struct Team {
-    const SolveParams &P;
-    // shared memory arrays: constant offsets (parameter bank) into the dynamic segment -- no registers, no 64-bit pointers
-    unsigned oF1;                // F1 operand of the vertex sum: P.so.F1 (tagged kernels) or P.so.F2
-#define sF1 ((const double *)(smem_raw + oF1))
-#define sF1_home ((double *)(smem_raw + P.so.F1))
-#define sF2 ((double *)(smem_raw + P.so.F2))
-#define sRho ((double *)(smem_raw + P.so.rho))
-#define sOff ((double *)(smem_raw + P.so.off))
-#define sWT ((double *)(smem_raw + P.so.wt))
-#define sOwn ((double *)(smem_raw + P.so.own))
-#define sPart ((double *)(smem_raw + P.so.part))
-#define sLane ((double *)(smem_raw + P.so.lane))
-#define sC ((double *)(smem_raw + P.so.C))
-#define sX ((double *)(smem_raw + P.so.X))
-#define sScan ((double *)(smem_raw + P.so.scan))
-#define sTab ((double *)(smem_raw + P.so.tab))
-#define sDesc ((int *)(smem_raw + P.so.desc))
-#define sAbort ((volatile int *)(smem_raw + P.so.misc))
-    // identity
-    int cta, tid, lane, warp;
-#define NkP (even_up(P.Nk))
-#define GP (even_up(P.G))
-#define EP (even_up(P.ent_max))
-#define RP (even_up(P.rows_max))
-    int row0, nrows;             // rows owned by this CTA: [row0, row0 + nrows)
-    int we0, we_n;               // first (warp,row) entry of this warp and how many it has
-    int eb0, eb1;                // owner thread tid < nrows: entries of its row
-    int owner[KPT];              // owner CTA of the rows this thread finishes (k = tid*KPT + j)
-    // register-resident part of the tables: the 12 values of this lane for the first UR units of the warp
-    double tab[UR > 0 ? UR : 1][kUV];
-    int udesc[UR > 0 ? UR : 1];
-    // exchange
-    double *xbase, *qbase;
-    unsigned epoch, qepoch;
-    double myoff1, myoff2, myoff3;   // offsets of this CTA from the last exchange
-    long long slab_base;         // first slot of this CTA in the team layout
-#ifdef MCT_PROFILE
-    long long prof[kProfSlots], tlast;
-#endif
-
-    __device__ __forceinline__ Team(const SolveParams &p) : P(p) {}
-    __device__ __forceinline__ bool aborted() const { return *sAbort != 0; }
-    // per-row constant of the row this thread owns (valid for tid < nrows)
-    __device__ __forceinline__ double own(int field) const { return sOwn[field * RP + (tid < nrows ? tid : 0)]; }
-    __device__ __forceinline__ void load_own(const EqDev &E) {
-        if (tid < nrows) {
-            const int k = row0 + tid;
-            sOwn[OWN_K * RP + tid] = E.kvec[k]; sOwn[OWN_F0 * RP + tid] = E.F0[k];
-            sOwn[OWN_AL * RP + tid] = E.alpha[k]; sOwn[OWN_BE * RP + tid] = E.beta[k];
-            sOwn[OWN_GA * RP + tid] = E.gamma[k]; sOwn[OWN_DE * RP + tid] = E.delta[k];
-            sOwn[OWN_K0 * RP + tid] = 0.0;
-        }
-    }
-
-    // ------------------------------------------------------------------------------------------ spin helpers
-    __device__ __forceinline__ bool spin_check(long long t0, unsigned &spins) {
-        if ((++spins & 255u) == 0) {
-            if (*(volatile int *)P.abort_flag) { *sAbort = 1; return true; }
-            if (clock64() - t0 > P.spin_limit_cycles) { atomicExch(P.abort_flag, 1); *sAbort = 1; return true; }
-        }
-        return false;
-    }
-
-    // ------------------------------------------------------------------------------------------ block helpers
-    __device__ __forceinline__ void warp_inscan3(double &v0, double &v1, double &v2) {
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            double u0 = __shfl_up_sync(0xffffffffu, v0, o), u1 = __shfl_up_sync(0xffffffffu, v1, o), u2 = __shfl_up_sync(0xffffffffu, v2, o);
-            if (lane >= o) { v0 += u0; v1 += u1; v2 += u2; }
-        }
-    }
-    // inclusive block scan of three per-thread values (all threads must call; one __syncthreads inside)
-    __device__ __forceinline__ void block_inscan3(double &v0, double &v1, double &v2) {
-        warp_inscan3(v0, v1, v2);
-        if (lane == 31) { sScan[warp] = v0; sScan[kWarps + warp] = v1; sScan[2 * kWarps + warp] = v2; }
-        __syncthreads();
-        double b0 = 0.0, b1 = 0.0, b2 = 0.0;
-        for (int w = 0; w < warp; w++) { b0 += sScan[w]; b1 += sScan[kWarps + w]; b2 += sScan[2 * kWarps + w]; }
-        v0 += b0; v1 += b1; v2 += b2;
-    }
-
-    // ------------------------------------------------------------------------------------------ kernel evaluation
-    // One unit (layout.cuh): 32 positions x 4 rows.  Every lane loads its single operand and the 4 consecutive window
-    // operands, forms the 4 products and feeds 12 FMAs with the 12 table values it owns.  When the unit starts a new
-    // (warp, row block) entry the 12 finished partials are parked in the warp scratch first (warp-uniform, rare).
-    // The operands of the NEXT unit are loaded before the arithmetic of this one (op/nop), otherwise every row waits
-    // for its own shared-memory load.
-    struct Operands { double f1, w[kRB]; };
-    __device__ __forceinline__ void load_operands(int d, Operands &o) const {
-        const double *S = (d & kUSwap) ? (const double *)sF2 : sF1, *W = (d & kUSwap) ? sF1 : (const double *)sF2;
-        o.f1 = S[(d & ((1 << kUA0Bits) - 1)) + lane];
-        const double *wp = W + (((d >> kUW0Shift) & ((1 << kUW0Bits) - 1)) - kFPad) + ((d & kUNeg) ? -lane : lane);
-#pragma unroll
-        for (int r = 0; r < kRB; r++) o.w[r] = wp[r];
-    }
-    __device__ __forceinline__ void unit(int d, const Operands &o, const double (&t)[kUV], double (&acc)[kUV], double *&sl) {
-        if (d & kUNewEntry) {
-#pragma unroll
-            for (int v = 0; v < kUV; v++) { sl[v * kLaneStride] = acc[v]; acc[v] = 0.0; }
-            sl += kUV * kLaneStride;
-        }
-        // rows of the block that do not exist (a trailing block of the CTA's range) are skipped: warp-uniform branches
-        const int nr = (d >> kURowsShift) & 3;
-        { const double f = o.f1 * o.w[0]; acc[0] = fma(t[0], f, acc[0]); acc[1] = fma(t[1], f, acc[1]); acc[2] = fma(t[2], f, acc[2]); }
-        if (nr >= 1) { const double f = o.f1 * o.w[1]; acc[3] = fma(t[3], f, acc[3]); acc[4] = fma(t[4], f, acc[4]); acc[5] = fma(t[5], f, acc[5]); }
-        if (nr >= 2) { const double f = o.f1 * o.w[2]; acc[6] = fma(t[6], f, acc[6]); acc[7] = fma(t[7], f, acc[7]); acc[8] = fma(t[8], f, acc[8]); }
-        if (nr >= 3) { const double f = o.f1 * o.w[3]; acc[9] = fma(t[9], f, acc[9]); acc[10] = fma(t[10], f, acc[10]); acc[11] = fma(t[11], f, acc[11]); }
-    }
-
-    // evaluate_kernel!(K, kernel, F, t) for the whole team (src/Kernels/ModeCouplingKernels.jl:211-228, 450-467),
-    // up to the prefix sums inside this CTA.  Inputs: sF1 (collective F at this time for tagged kernels, == sF2
-    // otherwise) and sF2 (current iterate), both complete and visible (caller synced).  Output, in owner thread
-    // tid < nrows: L_m = sum of the increments of rows row0 .. row0+tid  (so T_m[k] = off_m(cta) + L_m).
-    __device__ __forceinline__ void eval_rows(const double *__restrict__ gtab, double &L1, double &L2, double &L3) {
-        PROF(8);
-#ifdef MCT_PROFILE
-        if (epoch + 1 == (unsigned)P.snap_epoch) { long long g__; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g__)); prof[24] = g__; }
-#endif
-        {
-            double acc[kUV];
-#pragma unroll
-            for (int v = 0; v < kUV; v++) acc[v] = 0.0;
-            double *const sl0 = sLane + (size_t)warp * P.lane_cap * kUV * kLaneStride + lane;
-            double *sl = sl0;
-            const int US = P.US;
-            const int UG = P.U - UR - US;           // units that fit neither registers nor shared memory: from L2
-            Operands op, nop;
-            int dn = (UR > 0) ? udesc[0] : (US > 0 ? sDesc[warp * US] : (UG > 0 ? __ldg(P.udesc + slab_base + (long long)warp * P.U) : 0));
-            load_operands(dn, op);
-#ifdef MCT_PROFILE
-            if (!(P.dbg & 256))
-#endif
-#pragma unroll
-            for (int u = 0; u < UR; u++) {
-                const int d = dn;
-                dn = (u + 1 < UR) ? udesc[u + 1] : (US > 0 ? sDesc[warp * US] : (UG > 0 ? __ldg(P.udesc + slab_base + (long long)warp * P.U + UR) : 0));
-                load_operands(dn, nop);
-                unit(d, op, tab[u], acc, sl);
-                op = nop;
-            }
-#ifdef MCT_PROFILE
-            if (!(P.dbg & 512))
-#endif
-            for (int u = 0; u < US; u++) {
-                double t[kUV];
-                const double *ts = sTab + ((size_t)(warp * US + u) * kUV) * 32 + lane;
-#pragma unroll
-                for (int v = 0; v < kUV; v++) t[v] = ts[v * 32];
-                const int d = dn;
-                dn = (u + 1 < US) ? sDesc[warp * US + u + 1] : (UG > 0 ? __ldg(P.udesc + slab_base + (long long)warp * P.U + UR + US) : 0);
-                load_operands(dn, nop);
-                unit(d, op, t, acc, sl);
-                op = nop;
-            }
-            for (int u = 0; u < UG; u++) {
-                const long long slot = slab_base + (long long)warp * P.U + UR + US + u;
-                double t[kUV];
-                const double *ts = gtab + (slot * kUV) * 32 + lane;
-#pragma unroll
-                for (int v = 0; v < kUV; v++) t[v] = __ldg(ts + v * 32);
-                const int d = dn;
-                dn = (u + 1 < UG) ? __ldg(P.udesc + slot + 1) : 0;
-                load_operands(dn, nop);
-                unit(d, op, t, acc, sl);
-                op = nop;
-            }
-            // last entry, then lanes add the 32 lane partials of the 12*we_n columns
-            if (we_n > 0) {
-#pragma unroll
-                for (int v = 0; v < kUV; v++) sl[v * kLaneStride] = acc[v];
-            }
-            __syncwarp();
-#ifdef MCT_PROFILE
-            if (!(P.dbg & 128))
-#endif
-            for (int c = lane; c < kUV * we_n; c += 32) {
-                const double *col = sl0 - lane + (size_t)c * kLaneStride;
-                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-#pragma unroll
-                for (int i = 0; i < 32; i += 4) { s0 += col[i]; s1 += col[i + 1]; s2 += col[i + 2]; s3 += col[i + 3]; }
-                sPart[we0 * kUV + c] = (s0 + s1) + (s2 + s3);
-            }
-        }
-        PROF(0);
-        __syncthreads();
-        PROF(1);
-        // increments of the owned rows, inclusive prefix over them
-        double i1 = 0.0, i2 = 0.0, i3 = 0.0;
-        if (tid < nrows) {
-            const int r3 = 3 * (tid & (kRB - 1));          // row inside its row block
-            for (int e = eb0; e < eb1; e++) { i1 += sPart[e * kUV + r3]; i2 += sPart[e * kUV + r3 + 1]; i3 += sPart[e * kUV + r3 + 2]; }
-        }
-        if (P.rows_max <= 32) { if (warp == 0) warp_inscan3(i1, i2, i3); }
-        else block_inscan3(i1, i2, i3);
-        L1 = i1; L2 = i2; L3 = i3;
-        PROF(2);
-#ifdef MCT_PROFILE
-        if (epoch + 1 == (unsigned)P.snap_epoch) { long long g__; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g__)); prof[25] = g__; }
-#endif
-    }
-
-    // K = k T1 + T2/k^3 + T3/k   (:224-227) for the owned row, from the prefix inside the CTA and the CTA's offset
-    // (myoff_m: offsets of this CTA as of the last exchange, kept in registers because sOff is rewritten by the next one)
-    __device__ __forceinline__ double K_exact(double L1, double L2, double L3) const {
-        const double kval = own(OWN_K);
-        const double T1 = myoff1 + L1, T2 = myoff2 + L2, T3 = myoff3 + L3;
-        return kval * T1 + T2 / (kval * kval * kval) + T3 / kval;
-    }
-
-    // ------------------------------------------------------------------------------------------ exchange
-    // offset of CTA c (exclusive prefix of the block totals, written by the scanning warps of the last exchange)
-    __device__ __forceinline__ void cta_offsets(int c, double &o1, double &o2, double &o3) const {
-        o1 = sOff[c]; o2 = sOff[GP + c]; o3 = sOff[2 * GP + c];
-    }
-
-    // All-gather.  Owner threads publish `v` for their row; the last owner thread also publishes the CTA's block
-    // totals (B1,B2,B3).  Every thread collects the rows k = tid*KPT + j, every CTA scans the totals into sOff.
-    //   X_USE_OFF: out = v_k - (rho_1[k] off_1 + rho_2[k] off_2 + rho_3[k] off_3) with the offsets of k's owner
-    //   X_TRACK:   compare with fold (find_error, src/HelperFunctions.jl:55-64; F_old .= F, TimeDoublingSolver.jl:414)
-    //   dst:       shared array receiving out (or nullptr)
-    // Returns non-zero iff some |out - fold| > tol (identical in every thread of every CTA).  Ends with a barrier.
-    __device__ __forceinline__ int exchange(double v, double B1, double B2, double B3, int flags, double (&fold)[KPT], double *dst,
-                                            double (&out)[KPT]) {
-        PROF(3);
-        unsigned long long w[KPT];
-        if (P.G == 1) {
-            if (tid < nrows) sX[tid] = v;
-            __syncthreads();
-#pragma unroll
-            for (int j = 0; j < KPT; j++) { const int k = tid * KPT + j; w[j] = (k < P.Nk) ? (unsigned long long)__double_as_longlong(sX[k]) : 0ull; }
-            PROF(5);
-        } else {
-            epoch++;
-            double *cur = xbase + (size_t)(epoch & 3u) * P.xbuf_words, *clr = xbase + (size_t)((epoch + 2u) & 3u) * P.xbuf_words;
-#ifdef MCT_PROFILE
-#define SNAP(i) do { if (epoch == (unsigned)P.snap_epoch) { long long g__; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g__)); prof[i] = g__; } } while (0)
-#else
-#define SNAP(i) do { } while (0)
-#endif
-            SNAP(19);
-            if (tid < nrows) st_relaxed(cur + 4 * P.G + row0 + tid, v);
-            if (tid == nrows - 1) { st_relaxed2(cur + 4 * cta, B1, B2); st_relaxed2(cur + 4 * cta + 2, B3, 0.0); }
-            if (tid < nrows) st_relaxed_bits(clr + 4 * P.G + row0 + tid, kSentinel);
-            if (tid == nrows - 1) { st_relaxed2_bits(clr + 4 * cta, kSentinel, kSentinel); st_relaxed2_bits(clr + 4 * cta + 2, kSentinel, kSentinel); }
-            const long long t0 = clock64();
-            unsigned spins = 0;
-            PROF(4);
-            // Arrival: every CTA bumps one counter after publishing and ONE thread per CTA polls it; everybody else waits
-            // at named barrier 1 without issuing.  (Polling the data words from many threads floods the ~100 hot L2
-            // lines with retries as soon as the CTAs drift apart: the L2 round trip then grows to microseconds and the
-            // exchange never recovers -- profiles/exchange_notes.md.)  The counter is only a hint: no fence orders it
-            // after the data, the words still validate themselves.
-            if (warp == 0) {
-                __syncwarp();
-                if (lane == 0) {
-                    unsigned long long *ctr = (unsigned long long *)(xbase + 4 * (size_t)P.xbuf_words);
-                    asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(ctr), "l"(1ull) : "memory");
-                    const unsigned long long want = (unsigned long long)P.G * epoch;
-                    while (ld_relaxed_bits((const double *)ctr) < want) { if (spin_check(t0, spins)) break; }
-                }
-                __syncwarp();
-            }
-            asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory");
-            SNAP(20);
-            PROF(5);
-            // one shot: rows for every thread, block totals for thread t < G; re-issue only what still shows the sentinel
-            const double *src = cur + 4 * P.G + tid * KPT;
-            const int nv = min(KPT, P.Nk - tid * KPT);     // rows of this thread that exist (<= 0: none)
-            unsigned long long t0w = 0, t1w = 0, t2w = 0, t3w = 0;
-            const double *tsrc = cur + 4 * tid;
-            const bool tot = tid < P.G;
-            if (KPT == 1) {
-                if (nv > 0) w[0] = ld_relaxed_bits(src);
-            } else {
-#pragma unroll
-                for (int j = 0; j < KPT; j += 2) if (j < nv) ld_relaxed2_bits(src + j, w[j], w[j + 1]);
-            }
-            if (tot) { ld_relaxed2_bits(tsrc, t0w, t1w); ld_relaxed2_bits(tsrc + 2, t2w, t3w); }
-            while (true) {
-                bool again = false;
-                if (KPT == 1) {
-                    if (nv > 0 && w[0] == kSentinel) { w[0] = ld_relaxed_bits(src); again = true; }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < KPT; j += 2)
-                        if (j < nv && (w[j] == kSentinel || (j + 1 < nv && w[j + 1] == kSentinel))) { ld_relaxed2_bits(src + j, w[j], w[j + 1]); again = true; }
-                }
-                if (tot) {
-                    if (t0w == kSentinel || t1w == kSentinel) { ld_relaxed2_bits(tsrc, t0w, t1w); again = true; }
-                    if (t2w == kSentinel || t3w == kSentinel) { ld_relaxed2_bits(tsrc + 2, t2w, t3w); again = true; }
-                }
-                if (!again || spin_check(t0, spins)) break;
-            }
-            SNAP(21);
-            if (tid < 32 * kMaxTotWarps && warp * 32 < P.G) {
-                // exclusive prefix of the G block totals in a fixed order: inside each warp of 32 CTAs, then the totals of
-                // the warps before (named barrier 2 among the <= 5 scanning warps)
-                const double b1 = bits2d(t0w), b2 = bits2d(t1w), b3 = bits2d(t2w);
-                double s1 = b1, s2 = b2, s3 = b3;
-                warp_inscan3(s1, s2, s3);
-                if (lane == 31) { sWT[warp] = s1; sWT[8 + warp] = s2; sWT[16 + warp] = s3; }
-                const int nscan = ((P.G + 31) >> 5) * 32;
-                asm volatile("bar.sync 2, %0;" ::"r"(nscan) : "memory");
-                double w1 = 0.0, w2 = 0.0, w3 = 0.0;
-                for (int ww = 0; ww < warp; ww++) { w1 += sWT[ww]; w2 += sWT[8 + ww]; w3 += sWT[16 + ww]; }
-                // (an inclusive scan minus the own value is not bit-identical to an exclusive scan, but it is the
-                //  same numbers in every CTA, which is all that is required)
-                if (tot) { sOff[tid] = w1 + (s1 - b1); sOff[GP + tid] = w2 + (s2 - b2); sOff[2 * GP + tid] = w3 + (s3 - b3); }
-            }
-            __syncthreads();
-        }
-        PROF(6);
-        SNAP(22);
-        cta_offsets(cta, myoff1, myoff2, myoff3);
-        int pred = 0;
-#pragma unroll
-        for (int j = 0; j < KPT; j++) {
-            const int k = tid * KPT + j;
-            double f = bits2d(w[j]);
-            if (k < P.Nk) {
-#ifdef MCT_PROFILE
-                if ((flags & X_USE_OFF) && !(P.dbg & 64)) {
-                    double o1, o2, o3;
-                    if (P.dbg & 32) { o1 = myoff1; o2 = myoff2; o3 = myoff3; } else cta_offsets(owner[j], o1, o2, o3);
-#else
-                if (flags & X_USE_OFF) {
-                    double o1, o2, o3;
-                    cta_offsets(owner[j], o1, o2, o3);
-#endif
-                    f = f - (sRho[k] * o1 + sRho[NkP + k] * o2 + sRho[2 * NkP + k] * o3);
-                }
-                if (flags & X_TRACK) { pred |= (fabs(f - fold[j]) > P.tol) ? 1 : 0; fold[j] = f; }
-                if (dst) dst[k] = f;
-            }
-            out[j] = f;
-        }
-        const int any = __syncthreads_or(pred);
-        PROF(7);
-        SNAP(23);
-        return any;
-    }
-
-#ifdef MCT_PROFILE
-    // bare-bones copy of scripts/xchg_bench4.cu 'packed' for bisection
-    __device__ __forceinline__ unsigned long long exchange_min(double v) {
-        epoch++;
-        double *cur = xbase + (size_t)(epoch & 3u) * P.xbuf_words, *clr = xbase + (size_t)((epoch + 2u) & 3u) * P.xbuf_words;
-        const int pub = (P.dbg & 32) ? nrows - 1 : 0;
-        const bool snap = false;
-        if (tid < nrows) st_relaxed(cur + 4 * P.G + row0 + tid, v);
-        if (tid == pub) { st_relaxed2(cur + 4 * cta, v, v); st_relaxed2(cur + 4 * cta + 2, v, 0.0); }
-        if (tid < nrows) st_relaxed_bits(clr + 4 * P.G + row0 + tid, kSentinel);
-        if (tid == pub) { st_relaxed2_bits(clr + 4 * cta, kSentinel, kSentinel); st_relaxed2_bits(clr + 4 * cta + 2, kSentinel, kSentinel); }
-        if (P.dbg & 256) asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory"); else __syncthreads();
-        const long long t0 = clock64();
-        if (P.dbg & 512) __nanosleep(300); else { while (clock64() - t0 < 300) {} }
-        const double *src = cur + 4 * P.G + 4 * tid;
-        unsigned long long w0 = 0, w1 = 0, w2 = 0, w3 = 0;
-        const int nv = min(4, P.Nk - 4 * tid);
-        unsigned spins = 0;
-        if (nv > 0) ld_relaxed2_bits(src, w0, w1);
-        if (nv > 2) ld_relaxed2_bits(src + 2, w2, w3);
-        bool again = true;
-        while (again) {
-            again = false;
-            if (nv > 0 && (w0 == kSentinel || (nv > 1 && w1 == kSentinel))) { ld_relaxed2_bits(src, w0, w1); again = true; }
-            if (nv > 2 && (w2 == kSentinel || (nv > 3 && w3 == kSentinel))) { ld_relaxed2_bits(src + 2, w2, w3); again = true; }
-            if ((P.dbg & 64) && again && spin_check(t0, spins)) break;
-        }
-        unsigned long long a = 0, b = 0, c = 0, d = 0;
-        if (tid < P.G) {
-            const double *ts = cur + 4 * tid;
-            ld_relaxed2_bits(ts, a, b); ld_relaxed2_bits(ts + 2, c, d);
-            while (a == kSentinel || b == kSentinel || c == kSentinel || d == kSentinel) {
-                if (a == kSentinel || b == kSentinel) ld_relaxed2_bits(ts, a, b);
-                if (c == kSentinel || d == kSentinel) ld_relaxed2_bits(ts + 2, c, d);
-                if ((P.dbg & 64) && spin_check(t0, spins)) break;
-            }
-        }
-        if (P.dbg & 128) {
-            long long ta = clock64();
-            prof[14] += ta - t0;
-            if (snap) { long long g; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g)); prof[20] = g; }
-            if (tid < 32 * kMaxTotWarps && warp * 32 < P.G) {
-                const double b1 = bits2d(a), b2 = bits2d(b), b3 = bits2d(c);
-                double s1 = b1, s2 = b2, s3 = b3;
-                warp_inscan3(s1, s2, s3);
-                if (tid < P.G) { sOff[tid] = s1 - b1; sOff[GP + tid] = s2 - b2; sOff[2 * GP + tid] = s3 - b3; }
-                if (lane == 31) { sWT[warp] = s1; sWT[8 + warp] = s2; sWT[16 + warp] = s3; }
-            }
-            long long tb = clock64(); prof[15] += tb - ta;
-            __syncthreads();
-            long long tc = clock64(); prof[16] += tc - tb;
-            cta_offsets(cta, myoff1, myoff2, myoff3);
-            double o1, o2, o3;
-            cta_offsets(owner[0], o1, o2, o3);
-            w0 += (unsigned long long)(o1 + o2 + o3);
-            long long td = clock64(); prof[17] += td - tc;
-            const int r = __syncthreads_or((int)(w0 & 1));
-            long long te = clock64(); prof[18] += te - td;
-            if (snap) { long long g; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g)); prof[21] = g; }
-            return r + w0 + w1 + w2 + w3 + a + b + c + d;
-        }
-        __syncthreads();
-        __syncthreads();
-        return w0 + w1 + w2 + w3 + a + b + c + d;
-    }
-#endif
-
-    // ------------------------------------------------------------------------------------------ per-equation setup
-    __device__ __forceinline__ void load_tables(const EqDev &E) {
-#pragma unroll
-        for (int u = 0; u < UR; u++) {
-            const long long slot = slab_base + (long long)warp * P.U + u;
-#pragma unroll
-            for (int v = 0; v < kUV; v++) tab[u][v] = (u < P.U) ? __ldg(E.tab + (slot * kUV + v) * 32 + lane) : 0.0;
-        }
-        const int US = P.US;
-        for (int u = 0; u < US; u++) {
-            const long long slot = slab_base + (long long)warp * P.U + UR + u;
-            for (int v = 0; v < kUV; v++) sTab[((size_t)(warp * US + u) * kUV + v) * 32 + lane] = __ldg(E.tab + (slot * kUV + v) * 32 + lane);
-        }
-    }
-    // F1 operand of a tagged kernel (collective F at trajectory index tix); a later barrier publishes it.
-    __device__ __forceinline__ void load_F1(const EqDev &E, long long tix) {
-        if (E.Fc_traj == nullptr) return;
-        const double *src = E.Fc_traj + tix * P.Nk;
-        for (int k = tid; k < P.Nk; k += kThreads) sF1_home[k] = __ldg(src + k);
-    }
-
-    // ------------------------------------------------------------------------------------------ steady state
-    // solve_steady_state_mutable (src/SteadyStateMemoryEquation.jl:59-100) for a diagonal kernel:
-    // iterate F <- (K + gamma)^-1 K F0, K <- kernel(F) until max|F - F_old| <= tolerance.
-    __device__ __forceinline__ void steady_state_one(const EqDev &E) {
-        oF1 = P.so.F2;
-        load_tables(E);
-        load_own(E);
-        const int k = (tid < nrows) ? row0 + tid : -1;
-        const double f0 = (k >= 0) ? E.F0[k] : 0.0, g = (k >= 0) ? E.gamma[k] : 1.0;
-        double fold[KPT], out[KPT];
-#pragma unroll
-        for (int j = 0; j < KPT; j++) {
-            const int kk = tid * KPT + j;
-            fold[j] = (kk < P.Nk) ? E.F0[kk] : 0.0;              // Fold = copy(F0) :68
-            if (kk < P.Nk) sF2[kk] = fold[j];
-        }
-        __syncthreads();
-        double L1, L2, L3;
-        eval_rows(E.tab, L1, L2, L3);                          // K = evaluate_kernel(kernel, F0, t) :66
-        exchange(f0, L1, L2, L3, 0, fold, nullptr, out);
-        double K = K_exact(L1, L2, L3), Fn = f0;
-        long long iter = 0;
-        int status = MCT_OK;
-        while (true) {
-            iter++;
-            if (iter > P.max_iter) { status = MCT_NOT_CONVERGED; break; }   // :75-78
-            Fn = (K * f0) / (K + g);                           // :81-84
-            const int any = exchange(Fn, 0.0, 0.0, 0.0, X_TRACK, fold, sF2, out);   // find_error(F, Fold); Fold .= F  :90-91
-            eval_rows(E.tab, L1, L2, L3);                      // :89 (the error does not depend on it)
-            exchange(Fn, L1, L2, L3, 0, fold, nullptr, out);
-            K = K_exact(L1, L2, L3);
-            if (aborted()) { status = MCT_CUDA_ERROR; break; }
-            if (!any) break;
-        }
-        if (k >= 0) { E.F_out[k] = Fn; E.K_out[k] = K; }
-        if (cta == 0 && tid == 0) { *E.status = status; *E.kernel_evals = iter; }
-    }
-
-    // ------------------------------------------------------------------------------------------ time-doubling solve
-    __device__ __forceinline__ void solve_one(const EqDev &E) {
-        const int N = P.N, n4 = 4 * N, n2 = 2 * N;
-        enum { Ft = 0, Kt = 1, FI = 2, KI = 3 };          // F_temp, K_temp, F_I, K_I  (src/TimeDoublingSolver.jl:3-18)
-#define RING(R, k, s) E.ring[((size_t)(R) * P.Nk + (k)) * n4 + ((s) - 1)]   /* slot s is 1-based as in the reference */
-        oF1 = (E.Fc_traj != nullptr) ? P.so.F1 : P.so.F2;        // tagged kernels: A = V * Fc[iq] * Fs[ip]
-        load_tables(E);
-        load_own(E);
-        const int k = (tid < nrows) ? row0 + tid : -1;    // the wavenumber this thread owns (or -1)
-        double fold[KPT], out[KPT], L1, L2, L3;
-        // K0 = evaluate_kernel(kernel, F0, 0.0)   (src/MemoryEquation.jl:45)
-        for (int kk = tid; kk < P.Nk; kk += kThreads) sF2[kk] = E.F0[kk];
-        load_F1(E, 0);
-        __syncthreads();
-        eval_rows(E.tab, L1, L2, L3);
-        exchange(0.0, L1, L2, L3, 0, fold, nullptr, out);
-#ifdef MCT_PROFILE
-        {   // isolated cost of the two building blocks (cycles of thread 0, 2000 repetitions each)
-            long long c0 = clock64();
-            if (P.dbg & 16) { unsigned long long acc = 0; for (int i = 0; i < 2000; i++) acc += exchange_min(1.0 + i); if (acc == 12345) prof[13] = 1; }
-            else for (int i = 0; i < 2000; i++) exchange(1.0 + i, 0.0, 0.0, 0.0, 0, fold, nullptr, out);
-            long long c1 = clock64();
-            for (int i = 0; i < 2000; i++) { double l1, l2, l3; eval_rows(E.tab, l1, l2, l3); __syncthreads(); }
-            long long c2 = clock64();
-            for (int i = 0; i < 2000; i++) { double l1, l2, l3; eval_rows(E.tab, l1, l2, l3); exchange(l1, l1, l2, l3, X_USE_OFF | X_TRACK, fold, nullptr, out); }
-            long long c3 = clock64();
-            prof[10] = (c1 - c0) / 2000; prof[11] = (c2 - c1) / 2000; prof[12] = (c3 - c2) / 2000;
-            tlast = clock64();
-        }
-#endif
-        {
-            const double K0 = K_exact(L1, L2, L3), f0 = own(OWN_F0);
-            if (k >= 0) { sOwn[OWN_K0 * RP + tid] = K0; E.F_out[k] = f0; E.K_out[k] = K0; }     // output row 0 (t = 0)
-            // F_old = K0*F0 (:64) for every wavenumber
-            exchange(K0 * f0, 0.0, 0.0, 0.0, 0, fold, nullptr, out);
-        }
-#pragma unroll
-        for (int j = 0; j < KPT; j++) fold[j] = out[j];
-
-        // ---- bootstrap: 2N forward-Euler steps with the trapezoid memory integral
-        //      (initialize_F_temp_Euler! :96-109 -> src/EulerSolver.jl:26-64, 92-112); the dF history lives in the
-        //      F_I ring until initialize_integrals!.
-        const double de = P.dt0 / (4.0 * N);
-        if (k >= 0) RING(FI, k, 1) = E.dF0[k];
-        for (int it = 1; it <= n2; it++) {
-            double Fn = 0.0;
-            if (k >= 0) {
-                const double *dF = &RING(FI, k, 1);           // dF[j] = dF at Euler step j
-                const double K0 = own(OWN_K0), f0 = own(OWN_F0), al = own(OWN_AL), be = own(OWN_BE), ga = own(OWN_GA), de_k = own(OWN_DE);
-                double integ;
-                // integrand[i] = K_array[i] * dF_reverse[i], K_array[i] = K(t_{i-1}), dF_reverse[i] = dF(t_{it-i})
-                if (it == 1) {
-                    integ = (K0 * dF[0]) * de;                 // trapezoidal_integration it == 1 (EulerSolver.jl:34-36)
-                } else {
-                    double rr = (K0 * dF[it - 1]) / 2.0;
-                    rr += (RING(Kt, k, it - 1) * dF[0]) / 2.0;
-                    for (int i = 2; i <= it - 1; i++) rr += RING(Kt, k, i - 1) * dF[it - i];
-                    integ = rr * de;
-                }
-                const double Fo = (it == 1) ? f0 : RING(Ft, k, it - 1);
-                const double dFo = dF[it - 1];
-                double dFn;
-                if (P.second_order) {                          // Euler_step (EulerSolver.jl:55-58)
-                    const double ddF = (be * dFo + ga * Fo + de_k + integ) / (-al);
-                    dFn = dFo + de * ddF;
-                    Fn = Fo + de * dFn;
-                } else {                                       // :60-61
-                    dFn = (ga * Fo + de_k + integ) / (-be);
-                    Fn = Fo + de * dFn;
-                }
-                RING(Ft, k, it) = Fn;
-                RING(FI, k, it + 1) = dFn;
-            }
-            load_F1(E, it);
-            exchange(Fn, 0.0, 0.0, 0.0, 0, fold, sF2, out);
-            eval_rows(E.tab, L1, L2, L3);
-            exchange(Fn, L1, L2, L3, 0, fold, nullptr, out);
-            if (k >= 0) {
-                const double K = K_exact(L1, L2, L3);
-                RING(Kt, k, it) = K;                           // == initialize_K_temp! :155-166
-                E.F_out[(size_t)it * P.Nk + k] = Fn; E.K_out[(size_t)it * P.Nk + k] = K;
-            }
-            if (aborted()) return;
-        }
-        // initialize_integrals! :174-199 (overwrites the dF scratch, which is no longer needed)
-        if (k >= 0) {
-            const double F1v = RING(Ft, k, 1), K1v = RING(Kt, k, 1), K2v = RING(Kt, k, 2), f0 = own(OWN_F0);
-            double Fprev = F1v, Kprev = K1v;
-            RING(FI, k, 1) = (F1v + f0) / 2.0;
-            RING(KI, k, 1) = (3.0 * K1v - K2v) / 2.0;
-            for (int it = 2; it <= n2; it++) {
-                const double Fv = RING(Ft, k, it), Kv = RING(Kt, k, it);
-                RING(FI, k, it) = (Fv + Fprev) / 2.0;
-                RING(KI, k, it) = (Kv + Kprev) / 2.0;
-                Fprev = Fv; Kprev = Kv;
-            }
-        }
-        __syncthreads();
-
-        // ---- main loop: while solver.dt < 2 t_max (:523); block b works with dt = dt0 * 2^b
-        long long evals = 0;
-        int status = MCT_OK;
-        double Dt = P.dt0;
-        for (int blk = 0; blk < P.nblocks && status == MCT_OK; blk++, Dt *= 2.0) {
-            const double dl = Dt / (4.0 * N);
-            // C1 and C2 (:314-315) only change with the block: K_I[1], F_I[1] and dt are fixed inside it.  Every CTA
-            // needs rho_m[k] = (c2/c1) {k, 1/k^3, 1/k} of every wavenumber.
-            double c1 = 1.0, c2 = 0.0;
-            if (k >= 0) {
-                c1 = ((2.0 / (dl * dl) * own(OWN_AL) + 3.0 / (2.0 * dl) * own(OWN_BE)) + RING(KI, k, 1)) + own(OWN_GA);    // :314
-                c2 = RING(FI, k, 1) - own(OWN_F0);                                              // :315
-            }
-            exchange(c2 / c1, 0.0, 0.0, 0.0, 0, fold, nullptr, out);
-#pragma unroll
-            for (int j = 0; j < KPT; j++) {
-                const int kk = tid * KPT + j;
-                if (kk < P.Nk) {
-                    const double kv = E.kvec[kk];
-                    sRho[kk] = out[j] * kv; sRho[NkP + kk] = out[j] / (kv * kv * kv); sRho[2 * NkP + kk] = out[j] / kv;
-                }
-            }
-            __syncthreads();
-            for (int it = n2 + 1; it <= n4 && status == MCT_OK; it++) {
-                const int i2 = it / 2;
-                const long long row = 1 + (long long)n2 * (blk + 1) + (it - n2 - 1);
-                // update_Fuchs_parameters! :300-319 for the owned wavenumbers: one warp per row, lanes over the history
-                for (int r = warp; r < nrows; r += kWarps) {
-                    const int kr = row0 + r;
-                    double s1 = 0.0, s2 = 0.0;
-                    for (int j = 2 + lane; j <= i2; j += 32) s1 += (RING(Kt, kr, it - j) - RING(Kt, kr, it - j + 1)) * RING(FI, kr, j);        // :271-280
-                    for (int j = 2 + lane; j <= it - i2; j += 32) s2 += RING(KI, kr, j) * (RING(Ft, kr, it - j) - RING(Ft, kr, it - j + 1));  // :281-285
-                    s1 = warp_sum(s1); s2 = warp_sum(s2);
-                    if (lane == 0) { sC[r] = s1; sC[even_up(P.rows_max) + r] = s2; }
-                }
-                __syncthreads();
-                double Fc3 = 0.0, Finit = 0.0;
-                if (k >= 0) {
-                    const double al = own(OWN_AL), be = own(OWN_BE), de_k = own(OWN_DE);
-                    const double Fm1 = RING(Ft, k, it - 1), Fm2 = RING(Ft, k, it - 2), Fm3 = RING(Ft, k, it - 3);
-                    const double KI1 = RING(KI, k, 1), FI1 = RING(FI, k, 1);
-                    double v = al * ((5.0 * Fm1 - 4.0 * Fm2 + Fm3) / (dl * dl));                // :259-260
-                    v += be * (2.0 / dl * Fm1 - Fm2 / (2.0 * dl));                              // :263-264
-                    v -= RING(Kt, k, it - i2) * RING(Ft, k, i2);                                // :267
-                    v += RING(Kt, k, it - 1) * FI1;                                             // :268
-                    v += KI1 * Fm1;                                                             // :269
-                    v += sC[tid]; v += sC[even_up(P.rows_max) + tid];
-                    v -= de_k;                                                                  // :286
-                    const double c3 = v;
-                    Fc3 = c3 / c1;
-                    // update_F! :326-337 with the stale K_temp[it]: 2 K0 in the first block (:83), 0 afterwards (:485)
-                    const double Kst = (blk == 0) ? (own(OWN_K0) + own(OWN_K0)) : 0.0;
-                    Finit = (-(Kst * c2) + c3) / c1;
-                }
-                load_F1(E, row);
-                PROF(9);
-                exchange(Finit, 0.0, 0.0, 0.0, 0, fold, sF2, out);
-                // fixed-point loop :404-417
-                long long iter = 0;
-                while (true) {
-                    iter++;
-                    if (iter > P.max_iter) { status = MCT_NOT_CONVERGED; break; }                // :406-408
-                    eval_rows(E.tab, L1, L2, L3);                                               // update_K! :360-369
-                    const int kc = (k >= 0) ? k : 0;
-                    const double Floc = Fc3 - (sRho[kc] * L1 + sRho[NkP + kc] * L2 + sRho[2 * NkP + kc] * L3);   // update_F! :333-336, CTA-local part
-                    const int any = exchange(Floc, L1, L2, L3, X_USE_OFF | X_TRACK, fold, sF2, out);   // find_error + F_old .= F
-                    evals++;                                                                    // :416
-                    if (aborted()) { status = MCT_CUDA_ERROR; break; }
-                    if (!any) break;
-                }
-                if (status != MCT_OK) break;
-                // store the step + update_integrals! :377-384, allocate_results! :429-438 (owners)
-                if (k >= 0) {
-                    const double Fn = sF2[k], K = K_exact(L1, L2, L3);
-                    RING(Ft, k, it) = Fn; RING(Kt, k, it) = K;
-                    RING(FI, k, it) = (Fn + RING(Ft, k, it - 1)) / 2.0;
-                    RING(KI, k, it) = (K + RING(Kt, k, it - 1)) / 2.0;
-                    E.F_out[(size_t)row * P.Nk + k] = Fn; E.K_out[(size_t)row * P.Nk + k] = K;
-                }
-                __syncthreads();
-                PROF(9);
-            }
-            if (status != MCT_OK) break;
-            // new_time_mapping! :448-489 (owners, one warp per row; read everything of a chunk before writing it)
-            for (int r = warp; r < nrows; r += kWarps) {
-                const int kr = row0 + r;
-                for (int jb = 1; jb <= n2; jb += 32) {
-                    const int j = jb + lane;
-                    double a = 0, b = 0, d = 0, e = 0;
-                    if (j <= n2) {
-                        a = (RING(FI, kr, 2 * j) + RING(FI, kr, 2 * j - 1)) / 2.0;
-                        b = (RING(KI, kr, 2 * j) + RING(KI, kr, 2 * j - 1)) / 2.0;
-                        d = RING(Ft, kr, 2 * j);
-                        e = RING(Kt, kr, 2 * j);
-                    }
-                    __syncwarp();
-                    if (j <= n2) { RING(FI, kr, j) = a; RING(KI, kr, j) = b; RING(Ft, kr, j) = d; RING(Kt, kr, j) = e; }
-                    __syncwarp();
-                }
-                for (int j = n2 + 1 + lane; j <= n4; j += 32) { RING(FI, kr, j) = 0.0; RING(KI, kr, j) = 0.0; RING(Ft, kr, j) = 0.0; RING(Kt, kr, j) = 0.0; }
-            }
-            __syncthreads();
-        }
-        if (cta == 0 && tid == 0) { *E.status = status; *E.kernel_evals = evals; }
-#undef RING
-    }
-
-    // next equation of this team (dynamic queue); CTA 0 pops it and hands it to the others through a mailbox of
-    // self-validating slots (same rotation as the exchange buffers).
-    __device__ __forceinline__ int next_equation() {
-        int e;
-        volatile int *sm = (volatile int *)(sAbort + 1);
-        if (P.G == 1) {
-            if (tid == 0) sm[0] = atomicAdd(P.queue, 1);
-        } else {
-            qepoch++;
-            double *cur = qbase + (size_t)(qepoch & 3u) * 16, *clr = qbase + (size_t)((qepoch + 2u) & 3u) * 16;
-            if (tid == 0) {
-                if (cta == 0) { st_relaxed(cur, (double)atomicAdd(P.queue, 1)); st_relaxed_bits(clr, kSentinel); }
-                const long long t0 = clock64();
-                unsigned spins = 0;
-                unsigned long long v;
-                while ((v = ld_relaxed_bits(cur)) == kSentinel) { if (spin_check(t0, spins)) { v = 0; break; } }
-                sm[0] = (int)bits2d(v);
-            }
-        }
-        __syncthreads();
-        e = sm[0];
-        __syncthreads();
-        return e;
-    }
-};
-
-template <int KPT, int UR>
-__global__ void __launch_bounds__(kThreads, 1) td_sc_kernel(const SolveParams P) {
-    Team<KPT, UR> T(P);
-    T.tid = threadIdx.x; T.lane = T.tid & 31; T.warp = T.tid >> 5;
-    const int team = blockIdx.x / P.G;
-    T.cta = blockIdx.x % P.G;
-    T.epoch = 0; T.qepoch = 0;
-    T.xbase = P.xbuf + (size_t)team * P.xstride;
-    T.qbase = P.qbox + (size_t)team * 64;
-    T.oF1 = P.so.F1;
-    T.slab_base = (long long)T.cta * kWarps * P.U;          // first unit slot of this CTA
-#ifdef MCT_PROFILE
-    for (int i = 0; i < kProfSlots; i++) T.prof[i] = 0;
-    T.tlast = clock64();
-    const long long t_begin = T.tlast;
-    long long g_begin;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g_begin));
-#endif
-    // per-CTA slice of the layout geometry (identical for every equation of this launch)
-    {
-        T.row0 = P.cta_meta[4 * T.cta]; T.nrows = P.cta_meta[4 * T.cta + 1];
-        T.we0 = P.warp_ent[T.cta * (kWarps + 1) + T.warp];
-        T.we_n = P.warp_ent[T.cta * (kWarps + 1) + T.warp + 1] - T.we0;
-        const int *eb = P.ent_begin + (size_t)T.cta * (P.rb_max + 1);
-        T.eb0 = (T.tid < T.nrows) ? eb[T.tid / kRB] : 0;
-        T.eb1 = (T.tid < T.nrows) ? eb[T.tid / kRB + 1] : 0;
-#pragma unroll
-        for (int j = 0; j < KPT; j++) { const int k = T.tid * KPT + j; T.owner[j] = (k < P.Nk) ? P.row_owner[k] : 0; }
-#pragma unroll
-        for (int u = 0; u < UR; u++) T.udesc[u] = (u < P.U) ? P.udesc[T.slab_base + (long long)T.warp * P.U + u] : 0;
-        if (T.lane < P.US) ((int *)(smem_raw + P.so.desc))[T.warp * P.US + T.lane] = P.udesc[T.slab_base + (long long)T.warp * P.U + UR + T.lane];
-        // zero padding around the F arrays (window operands of padding lanes)
-        for (int i = T.tid; i < kFPad; i += kThreads) {
-            double *f1 = (double *)(smem_raw + P.so.F1), *f2 = (double *)(smem_raw + P.so.F2);
-            f1[-1 - i] = 0.0; f2[-1 - i] = 0.0; f1[P.Nk + i] = 0.0; f2[P.Nk + i] = 0.0;
-        }
-        for (int i = T.tid; i < 3 * even_up(P.G); i += kThreads) ((double *)(smem_raw + P.so.off))[i] = 0.0;
-        if (T.tid < 24) ((double *)(smem_raw + P.so.wt))[T.tid] = 0.0;
-        for (int i = T.tid; i < 3 * even_up(P.Nk); i += kThreads) ((double *)(smem_raw + P.so.rho))[i] = 0.0;
-        if (T.tid == 0) *(volatile int *)(smem_raw + P.so.misc) = 0;
-    }
-    __syncthreads();
-    while (true) {
-        const int e = T.next_equation();
-        if (e >= P.n_eq || T.aborted()) break;
-        {   // the equation descriptor lives in shared memory for the solve (keeps ~30 registers free)
-            const int *src = (const int *)(P.eqs + e);
-            int *dst = (int *)(smem_raw + P.so.eq);
-            if (T.tid < (int)(sizeof(EqDev) / 4)) dst[T.tid] = src[T.tid];
-        }
-        __syncthreads();
-        const EqDev &E = *(const EqDev *)(smem_raw + P.so.eq);
-        if (E.mode == 1) T.steady_state_one(E);
-        else T.solve_one(E);
-        if (T.aborted()) {
-            if (T.cta == 0 && T.tid == 0) *E.status = MCT_CUDA_ERROR;
-            break;
-        }
-        __syncthreads();
-    }
-#ifdef MCT_PROFILE
-    if (team == 0 && T.tid == 0 && P.prof) {
-        long long g_end;
-        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g_end));
-        T.prof[kProfSlots - 2] = clock64() - t_begin;
-        T.prof[kProfSlots - 1] = g_end - g_begin;
-        for (int i = 0; i < kProfSlots; i++) P.prof[T.cta * kProfSlots + i] = T.prof[i];
-    }
-#endif
-}
-
-#undef NkP
-#undef GP
-#undef EP
-#undef RP
-
-template <int KPT>
-void *pick_tr(int UR) {
-    switch (UR) {
-        case 0: return (void *)td_sc_kernel<KPT, 0>;
-        case 2: return (void *)td_sc_kernel<KPT, 2>;
-        case 3: return (void *)td_sc_kernel<KPT, 3>;
-        case 4: return (void *)td_sc_kernel<KPT, 4>;
-        default: return nullptr;
-    }
-}
-
-}  // namespace
-
-size_t td_sc_smem_bytes(const SolveParams &P) { return plan_smem(P.Nk, P.G, P.rows_max, P.ent_max, P.lane_cap, P.US).total; }
-
-int td_sc_max_reg_units() { return 4; }
+int td_sc_max_reg_units(int Nk) { return (Nk > 2 * kThreads) ? 2 : 4; }
 
 int td_sc_launch(const SolveParams &P, cudaStream_t stream) {
     const int KPT = (P.Nk + kThreads - 1) / kThreads;
     MCT_REQUIRE(KPT <= kMaxKPT, MCT_UNSUPPORTED, "Nk > 2048 is not supported by the persistent solver");
-    MCT_REQUIRE(P.G <= 32 * kMaxTotWarps, MCT_UNSUPPORTED, "team larger than 160 CTAs");
-    MCT_REQUIRE(P.rows_max <= kThreads, MCT_UNSUPPORTED, "more than 512 rows per CTA: use a larger team");
+    MCT_REQUIRE(P.G <= 160, MCT_UNSUPPORTED, "team larger than 160 CTAs");
+    MCT_REQUIRE(P.rows_max <= kThreads, MCT_UNSUPPORTED, "more rows per CTA than threads: use a larger team");
     const size_t smem = td_sc_smem_bytes(P);
     void *fn = nullptr;
-    if (KPT <= 1) fn = pick_tr<1>(P.UR);
-    else if (KPT <= 2) fn = pick_tr<2>(P.UR);
-    else fn = pick_tr<4>(P.UR);
+    if (KPT <= 1) fn = td_sc_entry_k1(P.UR);
+    else if (KPT <= 2) fn = td_sc_entry_k2(P.UR);
+    else if (KPT <= 4) fn = td_sc_entry_k4(P.UR);
+    else fn = td_sc_entry_k8(P.UR);
     MCT_REQUIRE(fn != nullptr, MCT_BAD_ARGUMENT, "internal: no kernel instantiation for this UR");
     MCT_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     SolveParams Pc = P;
-    Pc.so = plan_smem(P.Nk, P.G, P.rows_max, P.ent_max, P.lane_cap, P.US);
+    Pc.so = td_sc_plan_smem(P.Nk, P.G, P.rows_max, P.ent_max, P.lane_cap, P.US);
     void *args[] = {(void *)&Pc};
     dim3 grid(P.nteams * P.G), block(kThreads);
     if (P.G > 1) {

@@ -53,11 +53,15 @@ struct SolveParams {
 };
 
 constexpr int kProfSlots = 32;
+constexpr int kLaneStride = 33;                                    // padded lane column of the warp scratch
+enum { OWN_K = 0, OWN_F0, OWN_AL, OWN_BE, OWN_GA, OWN_DE, OWN_K0, kOwnFields };   // per-row constants of the owner, in shared memory
+__host__ __device__ inline int even_up(int n) { return (n + 1) & ~1; }
 
 // shared memory needed by a launch with these parameters; US = 0 gives the fixed part
 size_t td_sc_smem_bytes(const SolveParams &P);
-// largest UR the kernel is instantiated for
-int td_sc_max_reg_units();
+// largest UR worth using at this Nk (24 registers per register-resident unit; the instantiations that finish 4 or 8 rows
+// per thread have fewer registers to spare)
+int td_sc_max_reg_units(int Nk);
 int td_sc_launch(const SolveParams &P, cudaStream_t stream);
 
 }  // namespace mct

@@ -95,6 +95,22 @@ def test_eval_nonsymmetric_tables_tagged():
         pkg.evaluate_kernel(kern, Fs, 4)        # time not in the collective solution: tDict KeyError in the reference
 
 
+def test_large_grid_Nk2000_eval_and_short_solve():
+    """Largest supported grid of the single-component path (8 wavenumbers per thread in the update phase)."""
+    p = P.hard_spheres(2000, 0.51)
+    kern = gpu_kernel(p)
+    okern = O.sc3d(p["rho"], 1.0, 1.0, p["k"], p["Sk"])
+    got = pkg.evaluate_kernel(kern, p["Sk"], 0.0)
+    ref = okern.evaluate(p["Sk"])
+    assert _rel(got, ref) < 1e-10            # the reference-order recursion itself carries ~5e-12 at this size (BASELINE.md)
+    e = P.overdamped(p)
+    kw = dict(N=4, dt=1e-6, t_max=1e-3, tolerance=1e-10)
+    sol, solver = gpu_solve(p, e, kernel=kern, **kw)
+    refs = oracle_solve(p, e, kernel=okern, **kw)
+    assert np.max(np.abs(sol.F - refs["F"])) <= 1e-10
+    assert solver.kernel_evals == refs["kernel_evals"]
+
+
 def test_bad_grid_is_rejected():
     p = P.hard_spheres(32, 0.5)
     k = p["k"].copy(); k[5] *= 1.001
