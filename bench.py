@@ -39,6 +39,7 @@ NK = 1000
 ETA = 0.5155
 WORKLOAD = ("config3: hard-sphere MCT, Percus-Yevick S(k), Nk=1000, eta=0.5155 (near eta_c), overdamped, "
             "TimeDoublingSolver(N=32, dt=1e-10, t_max=1e10, tol=1e-10)")
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 34611712 + 26191872      # profiles/ncu_full_r01_td_sc_kernel.csv
 METRIC = "hs_mct_nk1000_kernel_evals_per_s"
 UNIT = "kernel evals/s"
 
@@ -353,11 +354,13 @@ def main():
             "e2e": {"value": e2e_evals_all / e2e_max, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "solve_wall_ms": 1e3 * e2e_max / args.steps},
             "gpu_launches": int(launches_all),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH,
                          "kernel": "td_sc_kernel (one persistent cooperative launch per solve)",
                          "algorithmic_bytes_per_eval": bytes_per_eval, "peak_source": peak_src,
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one td_sc_kernel launch, ncu --set full capture of "
+                                           "the Nk=1000 solve (profiles/ncu_full_r01_td_sc_kernel.csv); not re-measured by this run",
                          "note": "vertex tables stay in registers + shared memory for the whole solve; DRAM traffic per launch is "
-                                 "one table load + the trajectory store (see profiles/)"},
+                                 "one table load + the trajectory store, ~6000x less than the algorithmic bytes"},
             "clocks": clocks,
         }
         if not args.no_cpu_baseline:
