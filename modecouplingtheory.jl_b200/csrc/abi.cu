@@ -190,7 +190,7 @@ static int env_int(const char *name, int dflt) {
 struct Residency { int UR, US, lane_cap; };
 
 // How the U units of every warp are kept: UR in registers (a kernel instantiation), US in shared memory, rest in L2.
-static Residency choose_residency(const TeamLayout &L, size_t smem_optin) {
+static Residency choose_residency(const TeamLayout &L, size_t smem_optin, int fabric) {
     Residency r;
     // 24 registers per register-resident unit; the instantiation that finishes 4 rows per thread (Nk > 512) has 28
     // fewer registers to spare (measured: 2 units there, 4 otherwise, keeps spills out of the kernel)
@@ -200,6 +200,7 @@ static Residency choose_residency(const TeamLayout &L, size_t smem_optin) {
     r.lane_cap = std::max(1, L.went_max);               // one scratch column set per (warp, row block) entry
     SolveParams P{};
     P.Nk = L.Nk; P.G = L.G; P.rows_max = L.rows_max; P.ent_max = L.ent_max; P.lane_cap = r.lane_cap; P.US = 0;
+    P.fabric = fabric; P.xbuf_words = L.xbuf_words;
     const int want = std::max(0, L.U - r.UR);
     const size_t fixed = td_sc_smem_bytes(P);
     const size_t per_unit = (size_t)kWarps * (kUV * 32 * 8 + 4);
@@ -223,6 +224,9 @@ static int choose_geometry(mct_kernel_t h, int n_eq, TeamLayout **out, int *ntea
         // latency: as many CTAs as keep every warp busy with a couple of units per iteration
         const int target = env_int("MCT_TARGET_UNITS", 2);
         G = (int)std::min<long long>(g_cap, std::max<long long>(G_fit, (units + (long long)kWarps * target - 1) / ((long long)kWarps * target)));
+        // small problems: a team of up to 16 CTAs is a thread-block cluster (DSMEM exchange, ~3x cheaper than through L2),
+        // so spread down to one unit per warp
+        if (G <= 16 && env_int("MCT_CLUSTER", 1)) G = (int)std::min<long long>(std::min(16, g_cap), std::max<long long>(G, (units + kWarps - 1) / kWarps));
     } else {
         // throughput: the smallest team whose tables stay on chip (the exchange is a per-CTA cost)
         G = G_fit;
@@ -322,23 +326,30 @@ static int run_batch(int n, mct_equation_t *eqs, int mode, double tol, long long
         e.status = q->d_status; e.kernel_evals = q->d_evals;
     }
     SolveParams P{};
-    const Residency res = choose_residency(*L, h0->smem_optin);
+    const int fabric = (L->G > 1 && L->G <= 16 && env_int("MCT_CLUSTER", 1)) ? 1 : 0;
+    const Residency res = choose_residency(*L, h0->smem_optin, fabric);
     P.Nk = h0->Nk; P.G = L->G; P.N = eqs[0]->opts.N; P.nblocks = eqs[0]->nblocks; P.n_eq = n; P.nteams = nteams;
     P.second_order = eqs[0]->second_order;
     P.dt0 = eqs[0]->opts.dt; P.tol = tol; P.max_iter = max_iter;
     P.U = L->U; P.UR = res.UR; P.US = res.US; P.lane_cap = res.lane_cap;
     P.rows_max = L->rows_max; P.rb_max = L->rb_max; P.ent_max = L->ent_max;
     P.udesc = L->d_udesc; P.cta_meta = L->d_cta_meta; P.ent_begin = L->d_ent_begin; P.warp_ent = L->d_warp_ent; P.row_owner = L->d_row_owner;
-    P.xbuf_words = L->xbuf_words;
+    P.xbuf_words = L->xbuf_words; P.fabric = fabric;
     P.xstride = 4LL * L->xbuf_words + 16;      // four rotating buffers + the arrival counter (own line)
     P.poll_delay = env_int("MCT_POLL_DELAY", 300);
     P.poll_backoff = env_int("MCT_POLL_BACKOFF", 100);
     P.dbg = env_int("MCT_DBG", 0);
     P.snap_epoch = env_int("MCT_SNAP_EPOCH", 1000);
     P.spin_limit_cycles = (long long)env_int("MCT_SPIN_LIMIT_MS", 2000) * 2000000LL;
+    if (fabric == 1) {
+        const int maxc = td_sc_max_clusters(P);
+        MCT_REQUIRE(maxc >= 1, MCT_CUDA_ERROR, "thread-block cluster launch not possible for this team size");
+        nteams = std::max(1, std::min(nteams, maxc));
+        P.nteams = nteams;
+    }
     if (env_int("MCT_VERBOSE", 0))
-        fprintf(stderr, "[mct] Nk=%d sym=%d n_eq=%d: teams=%d x G=%d, U=%d units/warp (%d regs, %d smem, %d L2), rows/CTA<=%d, entries/warp<=%d, smem=%zu B\n",
-                P.Nk, h0->sym, n, nteams, P.G, P.U, std::min(P.U, P.UR), P.US, std::max(0, P.U - P.UR - P.US), P.rows_max, L->went_max, td_sc_smem_bytes(P));
+        fprintf(stderr, "[mct] Nk=%d sym=%d n_eq=%d: teams=%d x G=%d, U=%d units/warp (%d regs, %d smem, %d L2), rows/CTA<=%d, entries/warp<=%d, smem=%zu B, fabric=%s\n",
+                P.Nk, h0->sym, n, nteams, P.G, P.U, std::min(P.U, P.UR), P.US, std::max(0, P.U - P.UR - P.US), P.rows_max, L->went_max, td_sc_smem_bytes(P), P.fabric ? "cluster/DSMEM" : (P.G > 1 ? "L2" : "none"));
 
     // communication scratch: exchange buffers and queue mailboxes (all slots armed with the sentinel = 0xFF bytes),
     // queue, abort flag, equation table

@@ -10,7 +10,7 @@ void *td_sc_entry_k1(int UR);
 void *td_sc_entry_k2(int UR);
 void *td_sc_entry_k4(int UR);
 void *td_sc_entry_k8(int UR);
-SmemOffsets td_sc_plan_smem(int Nk, int G, int rows_max, int ent_max, int lane_cap, int US) {
+SmemOffsets td_sc_plan_smem(int Nk, int G, int rows_max, int ent_max, int lane_cap, int US, int fabric, int xbuf_words) {
     SmemOffsets p;
     size_t o = 0;
     const int NkP = even_up(Nk), NkF = even_up(Nk + 2 * kFPad);
@@ -30,6 +30,7 @@ SmemOffsets td_sc_plan_smem(int Nk, int G, int rows_max, int ent_max, int lane_c
     p.misc = (unsigned)o; o += 32;
     p.eq = (unsigned)o; o += (sizeof(EqDev) + 15) & ~(size_t)15;
     o = (o + 15) & ~(size_t)15;
+    p.xd = (unsigned)o; o += (fabric == 1) ? (size_t)4 * xbuf_words * 8 : 0;     // cluster fabric: the exchange buffers live here
     p.desc = (unsigned)o; o += (size_t)even_up(kWarps * US) * 4;
     o = (o + 15) & ~(size_t)15;
     p.tab = (unsigned)o; o += (size_t)kWarps * US * kUV * 32 * 8;
@@ -38,7 +39,7 @@ SmemOffsets td_sc_plan_smem(int Nk, int G, int rows_max, int ent_max, int lane_c
 }
 
 
-size_t td_sc_smem_bytes(const SolveParams &P) { return td_sc_plan_smem(P.Nk, P.G, P.rows_max, P.ent_max, P.lane_cap, P.US).total; }
+size_t td_sc_smem_bytes(const SolveParams &P) { return td_sc_plan_smem(P.Nk, P.G, P.rows_max, P.ent_max, P.lane_cap, P.US, P.fabric, P.xbuf_words).total; }
 
 int td_sc_max_reg_units(int Nk) { return (Nk > 2 * kThreads) ? 2 : 4; }
 
@@ -56,10 +57,20 @@ int td_sc_launch(const SolveParams &P, cudaStream_t stream) {
     MCT_REQUIRE(fn != nullptr, MCT_BAD_ARGUMENT, "internal: no kernel instantiation for this UR");
     MCT_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     SolveParams Pc = P;
-    Pc.so = td_sc_plan_smem(P.Nk, P.G, P.rows_max, P.ent_max, P.lane_cap, P.US);
+    Pc.so = td_sc_plan_smem(P.Nk, P.G, P.rows_max, P.ent_max, P.lane_cap, P.US, P.fabric, P.xbuf_words);
     void *args[] = {(void *)&Pc};
     dim3 grid(P.nteams * P.G), block(kThreads);
-    if (P.G > 1) {
+    if (P.fabric == 1) {
+        // one thread-block cluster per team: the hardware co-schedules the CTAs of a cluster, teams are independent
+        if (P.G > 8) MCT_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)P.G; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        MCT_CUDA(cudaLaunchKernelExC(&cfg, fn, args));
+    } else if (P.G > 1) {
         // the exchange spins on other CTAs of the team: a cooperative launch guarantees co-residency or fails.
         MCT_CUDA(cudaLaunchCooperativeKernel(fn, grid, block, args, smem, stream));
     } else {
@@ -69,4 +80,25 @@ int td_sc_launch(const SolveParams &P, cudaStream_t stream) {
     return MCT_OK;
 }
 
+}  // namespace mct
+
+namespace mct {
+// how many clusters of G CTAs with this much shared memory can be resident at once (0 if the launch is impossible)
+int td_sc_max_clusters(const SolveParams &P) {
+    const int KPT = (P.Nk + kThreads - 1) / kThreads;
+    void *fn = KPT <= 1 ? td_sc_entry_k1(P.UR) : KPT <= 2 ? td_sc_entry_k2(P.UR) : KPT <= 4 ? td_sc_entry_k4(P.UR) : td_sc_entry_k8(P.UR);
+    if (!fn) return 0;
+    const size_t smem = td_sc_smem_bytes(P);
+    if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+    if (P.G > 8 && cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); return 0; }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(P.G * 64); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)P.G; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, fn, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
 }  // namespace mct

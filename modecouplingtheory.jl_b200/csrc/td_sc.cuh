@@ -22,7 +22,7 @@ struct EqDev {
 // byte offsets of the kernel's arrays inside its dynamic shared memory (filled by td_sc_launch; kept in the
 // parameter bank so that they cost no registers)
 struct SmemOffsets {
-    unsigned F1, F2, rho, off, wt, own, part, lane, C, X, scan, misc, eq, desc, tab, total;
+    unsigned F1, F2, rho, off, wt, own, part, lane, C, X, scan, misc, eq, xd, desc, tab, total;
 };
 
 struct SolveParams {
@@ -38,6 +38,7 @@ struct SolveParams {
     // team communication
     double *xbuf;               // [nteams][4][xbuf_words]: rotating exchange buffers of self-validating 8-byte slots
     int xbuf_words;
+    int fabric;                 // 0: exchange through L2 (any team size); 1: the team is a thread-block cluster (G <= 16), DSMEM
     long long xstride;          // doubles per team: 4*xbuf_words + 16 (arrival counter)
     int poll_delay;             // ns between publishing and the first collecting load
     int poll_backoff;           // ns between two collecting attempts
@@ -63,5 +64,6 @@ size_t td_sc_smem_bytes(const SolveParams &P);
 // per thread have fewer registers to spare)
 int td_sc_max_reg_units(int Nk);
 int td_sc_launch(const SolveParams &P, cudaStream_t stream);
+int td_sc_max_clusters(const SolveParams &P);
 
 }  // namespace mct

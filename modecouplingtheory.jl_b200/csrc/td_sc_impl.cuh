@@ -55,6 +55,22 @@ __device__ __forceinline__ void ld_relaxed2_bits(const double *p, unsigned long 
 }
 __device__ __forceinline__ double bits2d(unsigned long long v) { return __longlong_as_double((long long)v); }
 
+// ---- thread-block cluster / distributed shared memory (teams of <= 16 CTAs exchange through DSMEM instead of L2)
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void st_cluster(unsigned local_addr, int rank, double v) {      // store into CTA `rank` of the cluster
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+    asm volatile("st.relaxed.cluster.shared::cluster.f64 [%0], %1;" ::"r"(r), "d"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_smem_relaxed_bits(const double *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.cluster.shared::cta.u64 %0, [%1];" : "=l"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 #ifdef MCT_PROFILE
 #define PROF(i) do { long long now__ = clock64(); prof[i] += now__ - tlast; tlast = now__; } while (0)
 #else
@@ -83,6 +99,7 @@ struct Team {
 #define sTab ((double *)(smem_raw + P.so.tab))
 #define sDesc ((int *)(smem_raw + P.so.desc))
 #define sAbort ((volatile int *)(smem_raw + P.so.misc))
+#define sXD ((double *)(smem_raw + P.so.xd))
     // identity
     int cta, tid, lane, warp;
 #define NkP (even_up(P.Nk))
@@ -296,6 +313,49 @@ struct Team {
 #pragma unroll
             for (int j = 0; j < KPT; j++) { const int k = tid * KPT + j; w[j] = (k < P.Nk) ? (unsigned long long)__double_as_longlong(sX[k]) : 0ull; }
             PROF(5);
+        } else if (P.fabric == 1) {
+            // ---- cluster fabric: the team is one thread-block cluster; every CTA owns a copy of the exchange buffers in its
+            //      shared memory and the publishers store straight into all of them (DSMEM).  Collecting is a local spin.
+            epoch++;
+            double *lcur = sXD + (size_t)(epoch & 3u) * P.xbuf_words, *lclr = sXD + (size_t)((epoch + 2u) & 3u) * P.xbuf_words;
+            // re-arm the own copy of the buffer used two exchanges from now (peers write it only after they have seen this
+            // CTA's data of the next exchange, which is published after the barrier that ends this one)
+            for (int i = tid; i < 4 * P.G + P.Nk; i += kThreads) ((unsigned long long *)lclr)[i] = kSentinel;
+            if (tid < nrows) {
+                const unsigned a = smem_u32(lcur + 4 * P.G + row0 + tid);
+                for (int p = 0; p < P.G; p++) st_cluster(a, p, v);
+            }
+            if (tid == nrows - 1) {
+                const unsigned a = smem_u32(lcur + 4 * cta);
+                for (int p = 0; p < P.G; p++) { st_cluster(a, p, B1); st_cluster(a + 8, p, B2); st_cluster(a + 16, p, B3); }
+            }
+            const long long t0 = clock64();
+            unsigned spins = 0;
+            PROF(4);
+            // arrival: lane t < G of warp 0 spins on the totals of CTA t in the LOCAL copy; every other warp waits at named
+            // barrier 1 without issuing (seven spinning warps would take the issue slots the publishing warp needs)
+            unsigned long long t0w = 0, t1w = 0, t2w = 0;
+            if (warp == 0 && tid < P.G) {
+                const double *ts = lcur + 4 * tid;
+                while ((t0w = ld_smem_relaxed_bits(ts)) == kSentinel) { if (spin_check(t0, spins)) break; }
+                while ((t1w = ld_smem_relaxed_bits(ts + 1)) == kSentinel) { if (spin_check(t0, spins)) break; }
+                while ((t2w = ld_smem_relaxed_bits(ts + 2)) == kSentinel) { if (spin_check(t0, spins)) break; }
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory");
+#pragma unroll
+            for (int j = 0; j < KPT; j++) {
+                const int k = tid * KPT + j;
+                w[j] = 0;
+                if (k < P.Nk) { while ((w[j] = ld_smem_relaxed_bits(lcur + 4 * P.G + k)) == kSentinel) { if (spin_check(t0, spins)) break; } }
+            }
+            PROF(5);
+            if (warp == 0) {     // G <= 16: one warp scans the totals
+                const double b1 = bits2d(t0w), b2 = bits2d(t1w), b3 = bits2d(t2w);
+                double s1 = b1, s2 = b2, s3 = b3;
+                warp_inscan3(s1, s2, s3);
+                if (tid < P.G) { sOff[tid] = s1 - b1; sOff[GP + tid] = s2 - b2; sOff[2 * GP + tid] = s3 - b3; }
+            }
+            __syncthreads();
         } else {
             epoch++;
             double *cur = xbase + (size_t)(epoch & 3u) * P.xbuf_words, *clr = xbase + (size_t)((epoch + 2u) & 3u) * P.xbuf_words;
@@ -805,8 +865,11 @@ __global__ void __launch_bounds__(kThreads, 1) td_sc_kernel(const SolveParams P)
         if (T.tid < 24) ((double *)(smem_raw + P.so.wt))[T.tid] = 0.0;
         for (int i = T.tid; i < 3 * even_up(P.Nk); i += kThreads) ((double *)(smem_raw + P.so.rho))[i] = 0.0;
         if (T.tid == 0) *(volatile int *)(smem_raw + P.so.misc) = 0;
+        if (P.fabric == 1)
+            for (int i = T.tid; i < 4 * P.xbuf_words; i += kThreads) ((unsigned long long *)(smem_raw + P.so.xd))[i] = kSentinel;
     }
     __syncthreads();
+    if (P.fabric == 1) cluster_sync_all();        // nobody stores into a peer before its buffers are armed
     while (true) {
         const int e = T.next_equation();
         if (e >= P.n_eq || T.aborted()) break;
@@ -825,6 +888,7 @@ __global__ void __launch_bounds__(kThreads, 1) td_sc_kernel(const SolveParams P)
         }
         __syncthreads();
     }
+    if (P.fabric == 1) cluster_sync_all();        // a CTA must not exit while peers may still store into its shared memory
 #ifdef MCT_PROFILE
     if (team == 0 && T.tid == 0 && P.prof) {
         long long g_end;
