@@ -54,7 +54,7 @@ struct SolveParams {
 };
 
 constexpr int kProfSlots = 32;
-constexpr int kLaneStride = 33;                                    // padded lane column of the warp scratch
+constexpr int kLaneStride = 17;                                    // padded column of the warp scratch: 16 half-warp partials
 enum { OWN_K = 0, OWN_F0, OWN_AL, OWN_BE, OWN_GA, OWN_DE, OWN_K0, kOwnFields };   // per-row constants of the owner, in shared memory
 __host__ __device__ inline int even_up(int n) { return (n + 1) & ~1; }
 

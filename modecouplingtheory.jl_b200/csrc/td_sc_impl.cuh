@@ -169,6 +169,15 @@ struct Team {
     // (warp, row block) entry the 12 finished partials are parked in the warp scratch first (warp-uniform, rare).
     // The operands of the NEXT unit are loaded before the arithmetic of this one (op/nop), otherwise every row waits
     // for its own shared-memory load.
+    // park the 12 lane partials of a finished entry: one butterfly step first, so that only 16 values per column go to
+    // shared memory (halves the scratch, which buys one more shared-memory-resident table unit at Nk = 1000)
+    __device__ __forceinline__ void park(const double (&acc)[kUV], double *sl) const {
+#pragma unroll
+        for (int v = 0; v < kUV; v++) {
+            const double x = acc[v] + __shfl_xor_sync(0xffffffffu, acc[v], 16);
+            if (lane < 16) sl[v * kLaneStride] = x;
+        }
+    }
     struct Operands { double f1, w[kRB]; };
     __device__ __forceinline__ void load_operands(int d, Operands &o) const {
         const double *S = (d & kUSwap) ? (const double *)sF2 : sF1, *W = (d & kUSwap) ? sF1 : (const double *)sF2;
@@ -179,8 +188,9 @@ struct Team {
     }
     __device__ __forceinline__ void unit(int d, const Operands &o, const double (&t)[kUV], double (&acc)[kUV], double *&sl) {
         if (d & kUNewEntry) {
+            park(acc, sl);
 #pragma unroll
-            for (int v = 0; v < kUV; v++) { sl[v * kLaneStride] = acc[v]; acc[v] = 0.0; }
+            for (int v = 0; v < kUV; v++) acc[v] = 0.0;
             sl += kUV * kLaneStride;
         }
         // rows of the block that do not exist (a trailing block of the CTA's range) are skipped: warp-uniform branches
@@ -204,7 +214,7 @@ struct Team {
             double acc[kUV];
 #pragma unroll
             for (int v = 0; v < kUV; v++) acc[v] = 0.0;
-            double *const sl0 = sLane + (size_t)warp * P.lane_cap * kUV * kLaneStride + lane;
+            double *const sl0 = sLane + (size_t)warp * P.lane_cap * kUV * kLaneStride + (lane & 15);
             double *sl = sl0;
             const int US = P.US;
             const int UG = P.U - UR - US;           // units that fit neither registers nor shared memory: from L2
@@ -248,20 +258,14 @@ struct Team {
                 unit(d, op, t, acc, sl);
                 op = nop;
             }
-            // last entry, then lanes add the 32 lane partials of the 12*we_n columns
-            if (we_n > 0) {
-#pragma unroll
-                for (int v = 0; v < kUV; v++) sl[v * kLaneStride] = acc[v];
-            }
+            // last entry, then lanes add the 16 half-warp partials of the 12*we_n columns
+            if (we_n > 0) park(acc, sl);
             __syncwarp();
-#ifdef MCT_PROFILE
-            if (!(P.dbg & 128))
-#endif
             for (int c = lane; c < kUV * we_n; c += 32) {
-                const double *col = sl0 - lane + (size_t)c * kLaneStride;
+                const double *col = sl0 - (lane & 15) + (size_t)c * kLaneStride;
                 double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
-                for (int i = 0; i < 32; i += 4) { s0 += col[i]; s1 += col[i + 1]; s2 += col[i + 2]; s3 += col[i + 3]; }
+                for (int i = 0; i < 16; i += 4) { s0 += col[i]; s1 += col[i + 1]; s2 += col[i + 2]; s3 += col[i + 3]; }
                 sPart[we0 * kUV + c] = (s0 + s1) + (s2 + s3);
             }
         }
