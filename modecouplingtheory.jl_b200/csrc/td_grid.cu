@@ -89,49 +89,51 @@ struct Ctx {
         lane = threadIdx.x & 31; gwarp = gtid >> 5; gwarps = gthreads >> 5;
     }
 
-    // line sums of this rank's lines (L = rank, rank + world, ...; line lengths vary smoothly with L, so the interleave
-    // balances); NS is a template parameter so that the 3*NS*NS accumulators live in registers
-    template <int NS>
+    // Line sums of this rank's lines (L = rank, rank + world, ...; line lengths vary smoothly with L, so the interleave
+    // balances).  The work is split by species pair e = (a,b) FIRST: a block stages the four operand vectors of ITS e
+    // (F, G1, G2, G3 along k: 32 Nk bytes) and the wavenumbers in shared memory and then walks lines reading only
+    // shared memory -- every operand is used by ~3 Nk lines, and re-reading them from L2 per entry made the walk
+    // L2-bandwidth bound (6 GB per evaluation at Ns=4, Nk=2000).
     __device__ void line_sums(const double *Fs, const double *G1, const double *G2, const double *G3, int nlines, size_t xwords) {
-        constexpr int NB = NS * NS;
+        extern __shared__ double gsm[];
         const int Nk = P.Nk, world = P.world, rank = P.rank;
-        double pab[NB];
-#pragma unroll
-        for (int e = 0; e < NB; e++) pab[e] = P.pref[e];
-        for (int Li = gwarp; Li * world + rank < nlines; Li += gwarps) {
+        const int e = blockIdx.x % nb;                       // species pair of this block
+        const int chunk = blockIdx.x / nb, nchunk = (gridDim.x - e + nb - 1) / nb;    // blocks sharing this e
+        double *sF = gsm, *s1 = gsm + Nk, *s2 = gsm + 2 * Nk, *s3 = gsm + 3 * Nk, *sk = gsm + 4 * Nk;
+        for (int k = threadIdx.x; k < Nk; k += blockDim.x) {
+            sF[k] = Fs[(size_t)e * Nk + k]; s1[k] = G1[(size_t)e * Nk + k]; s2[k] = G2[(size_t)e * Nk + k]; s3[k] = G3[(size_t)e * Nk + k];
+            sk[k] = P.kvec[k];
+        }
+        __syncthreads();
+        const double pab = P.pref[e];
+        const int warps_per_block = blockDim.x >> 5, wi = chunk * warps_per_block + (threadIdx.x >> 5), wstride = nchunk * warps_per_block;
+        for (int Li = wi; Li * world + rank < nlines; Li += wstride) {
             const int L = Li * world + rank;
-            double acc[3][NB];
-#pragma unroll
-            for (int e = 0; e < NB; e++) { acc[0][e] = 0.0; acc[1][e] = 0.0; acc[2][e] = 0.0; }
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0;
             const bool diag = L < 2 * Nk - 1;
             const int d = L - (Nk - 1), s = L - (2 * Nk - 1);
             const int q0 = diag ? max(0, -d) : 0, q1 = diag ? min(Nk, Nk - d) : s + 1;
             for (int iq = q0 + lane; iq < q1; iq += 32) {
                 const int ip = diag ? iq + d : s - iq;
-                const double q = P.kvec[iq], p = P.kvec[ip];
+                const double q = sk[iq], p = sk[ip];
                 const double pq2 = p * p - q * q;
                 const double P1 = p * q, P2 = p * q * (pq2 * pq2), P3 = 2.0 * p * q * pq2;
-#pragma unroll
-                for (int e = 0; e < NB; e++) {
-                    const size_t oq = (size_t)e * Nk + iq, op = (size_t)e * Nk + ip;
-                    const double t1 = Fs[oq] * G1[op], t2 = G2[op] * G3[oq], t3 = G2[oq] * G3[op], t4 = G1[oq] * Fs[op];
-                    acc[0][e] += (t1 + t2 + t3 + t4) * P1 * pab[e];      // :186-192
-                    acc[1][e] += (t1 - t2 - t3 + t4) * P2 * pab[e];
-                    acc[2][e] += (t1 - t4) * P3 * pab[e];
+                const double t1 = sF[iq] * s1[ip], t2 = s2[ip] * s3[iq], t3 = s2[iq] * s3[ip], t4 = s1[iq] * sF[ip];
+                a0 += (t1 + t2 + t3 + t4) * P1 * pab;      // :186-192
+                a1 += (t1 - t2 - t3 + t4) * P2 * pab;
+                a2 += (t1 - t4) * P3 * pab;
+            }
+            a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
+            if (lane == 0) {
+                const size_t w = (size_t)L * 3 * nb + e;
+                if (world == 1) { P.Lsum[w] = a0; P.Lsum[w + nb] = a1; P.Lsum[w + 2 * nb] = a2; }
+                else for (int r = 0; r < world; r++) {
+                    double *dst = P.xpeer[r] + (size_t)(xepoch & 3u) * xwords + w;
+                    st_relaxed_sys(dst, a0); st_relaxed_sys(dst + nb, a1); st_relaxed_sys(dst + 2 * nb, a2);
                 }
             }
-#pragma unroll
-            for (int m = 0; m < 3; m++)
-#pragma unroll
-                for (int e = 0; e < NB; e++) {
-                    const double v = warp_sum(acc[m][e]);
-                    if (lane == 0) {
-                        const size_t w = (size_t)L * 3 * NB + m * NB + e;
-                        if (world == 1) P.Lsum[w] = v;
-                        else for (int r = 0; r < world; r++) st_relaxed_sys(P.xpeer[r] + (size_t)(xepoch & 3u) * xwords + w, v);
-                    }
-                }
         }
+        __syncthreads();
     }
 
     // ---- K = kernel(F)  (ends with a grid barrier; Kout valid for every thread afterwards)
@@ -178,12 +180,7 @@ struct Ctx {
         xepoch++;
         double *lcur = (world > 1) ? P.xpeer[rank] + (size_t)(xepoch & 3u) * xwords : P.Lsum;
         // this rank's lines: L = rank, rank + world, ...  (line lengths vary smoothly with L, so the interleave balances)
-        switch (ns) {
-            case 1: line_sums<1>(Fs, G1, G2, G3, nlines, xwords); break;
-            case 2: line_sums<2>(Fs, G1, G2, G3, nlines, xwords); break;
-            case 3: line_sums<3>(Fs, G1, G2, G3, nlines, xwords); break;
-            default: line_sums<4>(Fs, G1, G2, G3, nlines, xwords); break;
-        }
+        line_sums(Fs, G1, G2, G3, nlines, xwords);
         if (world > 1) {
             // re-arm this rank's own copy of the buffer used two exchanges from now (every peer wrote it two exchanges ago
             // and will write it again only after it has seen this rank's data of the next exchange)
@@ -481,13 +478,16 @@ int ddim_build_table(int Nk, double prefactor, const double *dV, const double *d
 
 int td_grid_launch(const GridParams &P, int n_sm, cudaStream_t stream) {
     MCT_REQUIRE(P.ns >= 1 && P.ns <= kNsMax, MCT_UNSUPPORTED, "Ns > 4 is not supported on the device");
+    // multi-component: five vectors of Nk doubles per block in shared memory (line_sums)
+    const size_t smem = (P.type == GK_MC3D) ? (size_t)5 * P.Nk * sizeof(double) : 0;
+    MCT_CUDA(cudaFuncSetAttribute((void *)td_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    MCT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, td_grid_kernel, kGT, 0));
+    MCT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, td_grid_kernel, kGT, smem));
     MCT_REQUIRE(per_sm >= 1, MCT_CUDA_ERROR, "cooperative kernel does not fit");
     GridParams Pc = P;
     void *args[] = {(void *)&Pc};
     dim3 grid(n_sm * std::min(per_sm, 2)), block(kGT);
-    MCT_CUDA(cudaLaunchCooperativeKernel((void *)td_grid_kernel, grid, block, args, 0, stream));
+    MCT_CUDA(cudaLaunchCooperativeKernel((void *)td_grid_kernel, grid, block, args, smem, stream));
     count_launch();
     return MCT_OK;
 }
