@@ -463,7 +463,7 @@ static int grid_setup(mct_equation_t q, mct_kernel_t h, int mode, const std::vec
     const size_t traj = (mode == 0) ? (size_t)q->nt * dof : dof;
     const size_t lsum = (size_t)3 * Nk * 3 * nb;
     const size_t dfh = (mode == 0) ? (size_t)(2 * N + 1) * dof : 0;
-    const size_t total = 6 * dof + 4 * ring + 7 * dof + 4 * dof + 6 * dof + lsum + dfh + 2 * traj + 16;
+    const size_t total = 6 * dof + 4 * ring + 7 * dof + 4 * dof + 6 * dof + lsum + dfh + 2 * traj + 40;
     MCT_CUDA(cudaMalloc(&q->d_gws, total * sizeof(double)));
     MCT_CUDA(cudaMemset(q->d_gws, 0, total * sizeof(double)));
     MCT_CUDA(cudaMemcpy(q->d_gws, coef_host.data(), 6 * dof * sizeof(double), cudaMemcpyHostToDevice));
@@ -482,7 +482,7 @@ static int grid_setup(mct_equation_t q, mct_kernel_t h, int mode, const std::vec
     g.dFh = p; p += dfh;
     g.F_out = p; g.K_out = p + traj; p += 2 * traj;
     g.err = (unsigned long long *)p; p += 2;
-    g.status = (int *)p; g.kernel_evals = (long long *)(p + 2);
+    g.status = (int *)p; g.kernel_evals = (long long *)(p + 2); g.prof = (unsigned long long *)(p + 4);
     q->d_F = g.F_out; q->d_K = g.K_out;
     return MCT_OK;
 }
@@ -491,7 +491,7 @@ static int grid_run(mct_equation_t q, long long *evals, int *status, float *devi
     mct_kernel_t h = q->kernel;
     MCT_CUDA(cudaSetDevice(h->device));
     cudaStream_t s = h->stream;
-    MCT_CUDA(cudaMemsetAsync(q->gp.err, 0, 16 * sizeof(double), s));
+    MCT_CUDA(cudaMemsetAsync(q->gp.err, 0, 32 * sizeof(double), s));
     cudaEvent_t e0, e1;
     MCT_CUDA(cudaEventCreate(&e0)); MCT_CUDA(cudaEventCreate(&e1));
     MCT_CUDA(cudaEventRecord(e0, s));
@@ -506,6 +506,13 @@ static int grid_run(mct_equation_t q, long long *evals, int *status, float *devi
     int st = 0; long long ev = 0;
     MCT_CUDA(cudaMemcpy(&st, q->gp.status, sizeof(int), cudaMemcpyDeviceToHost));
     MCT_CUDA(cudaMemcpy(&ev, q->gp.kernel_evals, sizeof(long long), cudaMemcpyDeviceToHost));
+    if (env_int("MCT_GRID_PROF", 0)) {
+        unsigned long long pr[12];
+        MCT_CUDA(cudaMemcpy(pr, q->gp.prof, sizeof(pr), cudaMemcpyDeviceToHost));
+        fprintf(stderr, "[mct] grid phases (cycles of thread 0, %lld evals, %.3f ms):", ev, ms);
+        for (int i = 0; i < 12; i++) fprintf(stderr, " %llu", pr[i]);
+        fprintf(stderr, "\n");
+    }
     if (evals) *evals = ev;
     if (status) *status = st;
     return st;

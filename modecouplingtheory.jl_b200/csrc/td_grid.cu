@@ -25,44 +25,69 @@ namespace mct {
 namespace {
 
 constexpr int kGT = 256;        // threads per block
-constexpr int kNB = kNsMax * kNsMax;
 
-// C = A*B, column-major ns x ns, plain left-to-right sums (StaticArrays `*`)
-__device__ __forceinline__ void blk_mul(int ns, const double *A, const double *B, double *C) {
-    double tmp[kNB];
-    for (int j = 0; j < ns; j++)
-        for (int i = 0; i < ns; i++) {
-            double s = A[i] * B[j * ns];
-            for (int l = 1; l < ns; l++) s += A[i + l * ns] * B[l + j * ns];
-            tmp[i + j * ns] = s;
+// C = A*B, column-major NS x NS, plain left-to-right sums (StaticArrays `*`); everything stays in registers
+template <int NS>
+__device__ __forceinline__ void blk_mul(const double *A, const double *B, double *C) {
+    double tmp[NS * NS];
+#pragma unroll
+    for (int j = 0; j < NS; j++)
+#pragma unroll
+        for (int i = 0; i < NS; i++) {
+            double s = A[i] * B[j * NS];
+#pragma unroll
+            for (int l = 1; l < NS; l++) s += A[i + l * NS] * B[l + j * NS];
+            tmp[i + j * NS] = s;
         }
-    for (int e = 0; e < ns * ns; e++) C[e] = tmp[e];
+#pragma unroll
+    for (int e = 0; e < NS * NS; e++) C[e] = tmp[e];
 }
-// X = A \ B (ns right-hand sides), Gaussian elimination with partial pivoting
-__device__ __forceinline__ void blk_solve(int ns, const double *A, const double *B, double *X) {
-    if (ns == 1) { X[0] = B[0] / A[0]; return; }
-    double a[kNB], b[kNB];
-    for (int e = 0; e < ns * ns; e++) { a[e] = A[e]; b[e] = B[e]; }
-    for (int c = 0; c < ns; c++) {
-        int piv = c; double best = fabs(a[c + c * ns]);
-        for (int r = c + 1; r < ns; r++) if (fabs(a[r + c * ns]) > best) { best = fabs(a[r + c * ns]); piv = r; }
-        if (piv != c)
-            for (int j = 0; j < ns; j++) {
-                double t = a[c + j * ns]; a[c + j * ns] = a[piv + j * ns]; a[piv + j * ns] = t;
-                t = b[c + j * ns]; b[c + j * ns] = b[piv + j * ns]; b[piv + j * ns] = t;
+// x = A \ b for NR right-hand sides (columns of b), Gaussian elimination with partial pivoting.  The pivot row is
+// selected with predicated swaps so that every index is a compile-time constant (no local memory).
+template <int NS, int NR>
+__device__ __forceinline__ void blk_solve(const double *A, const double *B, double *X) {
+    if (NS == 1) {
+#pragma unroll
+        for (int j = 0; j < NR; j++) X[j] = B[j] / A[0];
+        return;
+    }
+    double a[NS * NS], b[NS * NR];
+#pragma unroll
+    for (int e = 0; e < NS * NS; e++) a[e] = A[e];
+#pragma unroll
+    for (int e = 0; e < NS * NR; e++) b[e] = B[e];
+#pragma unroll
+    for (int c = 0; c < NS; c++) {
+        int piv = c; double best = fabs(a[c + c * NS]);
+#pragma unroll
+        for (int r = c + 1; r < NS; r++) if (fabs(a[r + c * NS]) > best) { best = fabs(a[r + c * NS]); piv = r; }
+#pragma unroll
+        for (int r = c + 1; r < NS; r++)
+            if (piv == r) {
+#pragma unroll
+                for (int j = 0; j < NS; j++) { const double t = a[c + j * NS]; a[c + j * NS] = a[r + j * NS]; a[r + j * NS] = t; }
+#pragma unroll
+                for (int j = 0; j < NR; j++) { const double t = b[c + j * NS]; b[c + j * NS] = b[r + j * NS]; b[r + j * NS] = t; }
             }
-        for (int r = c + 1; r < ns; r++) {
-            const double f = a[r + c * ns] / a[c + c * ns];
-            if (f == 0.0) continue;
-            for (int j = c; j < ns; j++) a[r + j * ns] -= f * a[c + j * ns];
-            for (int j = 0; j < ns; j++) b[r + j * ns] -= f * b[c + j * ns];
+#pragma unroll
+        for (int r = c + 1; r < NS; r++) {
+            const double f = a[r + c * NS] / a[c + c * NS];
+            if (f != 0.0) {
+#pragma unroll
+                for (int j = c; j < NS; j++) a[r + j * NS] -= f * a[c + j * NS];
+#pragma unroll
+                for (int j = 0; j < NR; j++) b[r + j * NS] -= f * b[c + j * NS];
+            }
         }
     }
-    for (int j = 0; j < ns; j++)
-        for (int r = ns - 1; r >= 0; r--) {
-            double s = b[r + j * ns];
-            for (int c = r + 1; c < ns; c++) s -= a[r + c * ns] * X[c + j * ns];
-            X[r + j * ns] = s / a[r + r * ns];
+#pragma unroll
+    for (int j = 0; j < NR; j++)
+#pragma unroll
+        for (int r = NS - 1; r >= 0; r--) {
+            double s = b[r + j * NS];
+#pragma unroll
+            for (int c = r + 1; c < NS; c++) s -= a[r + c * NS] * X[c + j * NS];
+            X[r + j * NS] = s / a[r + r * NS];
         }
 }
 
@@ -77,28 +102,112 @@ __device__ __forceinline__ unsigned long long ld_relaxed_sys_bits(const double *
     return v;
 }
 
+// The solver context, compiled per species count so that all block algebra is unrolled into registers.
+//
+// Per-wavenumber work (block products, C1 \ rhs) is spread over "k groups": GW consecutive lanes of a warp own one
+// wavenumber, lane ge of the group owns element (ga, gb) of its Ns x Ns block; operands held by the other lanes of
+// the group come through shuffles, operands in memory are read directly (the 16 lanes of a group read one 128-byte
+// line).  The summation order of every product equals blk_mul's, so both forms give the same bits.
+template <int NS>
 struct Ctx {
+    static constexpr int NB = NS * NS;
+    static constexpr int GW = NS == 1 ? 1 : NS == 2 ? 4 : 16;      // lanes per wavenumber group
+    static constexpr int KPW = 32 / GW;                            // wavenumbers per warp
     const GridParams &P;
     cg::grid_group grid;
-    int nb, dof, gtid, gthreads, lane, gwarp, gwarps;
+    int dof, gtid, gthreads, lane, gwarp, gwarps;
+    int ge, ga, gb, gbase; bool gact;
     unsigned xepoch = 0;
     bool failed = false;
+    long long tp;
     __device__ Ctx(const GridParams &p) : P(p), grid(cg::this_grid()) {
-        nb = p.ns * p.ns; dof = p.Nk * nb;
+        dof = p.Nk * NB;
         gtid = blockIdx.x * blockDim.x + threadIdx.x; gthreads = gridDim.x * blockDim.x;
         lane = threadIdx.x & 31; gwarp = gtid >> 5; gwarps = gthreads >> 5;
+        const int l = lane % GW;
+        gbase = lane - l; gact = l < NB; ge = gact ? l : 0; ga = ge % NS; gb = ge / NS;
+        tp = clock64();
+    }
+    __device__ __forceinline__ void mark(int slot) {
+        if (gtid == 0) { const long long t = clock64(); P.prof[slot] += (unsigned long long)(t - tp); tp = t; }
+    }
+    // element idx of a block whose elements are spread over this lane's k group
+    __device__ __forceinline__ double sh(double v, int idx) const { return __shfl_sync(0xffffffffu, v, gbase + idx); }
+    // this lane's element of A*B: A, B blocks in memory / A in memory, B in the group's registers / A in registers, B in memory
+    __device__ __forceinline__ double mm_gg(const double *A, const double *B) const {
+        double s = A[ga] * B[gb * NS];
+#pragma unroll
+        for (int l = 1; l < NS; l++) s += A[ga + l * NS] * B[l + gb * NS];
+        return s;
+    }
+    __device__ __forceinline__ double mm_gr(const double *A, double v) const {
+        double s = A[ga] * sh(v, gb * NS);
+#pragma unroll
+        for (int l = 1; l < NS; l++) s += A[ga + l * NS] * sh(v, l + gb * NS);
+        return s;
+    }
+    __device__ __forceinline__ double mm_rg(double v, const double *B) const {
+        double s = sh(v, ga) * B[gb * NS];
+#pragma unroll
+        for (int l = 1; l < NS; l++) s += sh(v, ga + l * NS) * B[l + gb * NS];
+        return s;
+    }
+    // this lane's element of A \ T (A in memory, T spread over the group): every lane solves the column it sits in
+    __device__ __forceinline__ double solve_group(const double *A, double t) const {
+        if (NS == 1) return t / A[0];
+        double a[NB], b[NS], x[NS];
+#pragma unroll
+        for (int e = 0; e < NB; e++) a[e] = A[e];
+#pragma unroll
+        for (int r = 0; r < NS; r++) b[r] = sh(t, r + gb * NS);
+        blk_solve<NS, 1>(a, b, x);
+        double r = x[0];
+#pragma unroll
+        for (int i = 1; i < NS; i++) if (ga == i) r = x[i];
+        return r;
     }
 
-    // Line sums of this rank's lines (L = rank, rank + world, ...; line lengths vary smoothly with L, so the interleave
-    // balances).  The work is split by species pair e = (a,b) FIRST: a block stages the four operand vectors of ITS e
-    // (F, G1, G2, G3 along k: 32 Nk bytes) and the wavenumbers in shared memory and then walks lines reading only
-    // shared memory -- every operand is used by ~3 Nk lines, and re-reading them from L2 per entry made the walk
-    // L2-bandwidth bound (6 GB per evaluation at Ns=4, Nk=2000).
-    __device__ void line_sums(const double *Fs, const double *G1, const double *G2, const double *G3, int nlines, size_t xwords) {
+    // ---- (1) G1 = C'FC, G2 = C'F, G3 = FC of one wavenumber from the group's F (lane e holds F[e]), stored species-major
+    //      ([e][k]) together with a copy of F so that the line walk reads unit stride along k.  Called by whole warps.
+    __device__ __forceinline__ void g_block(int k, bool valid, double f) {
+        const int Nk = P.Nk;
+        const double *Ck = P.C + (size_t)k * NB;
+        double g3 = sh(f, ga) * Ck[gb * NS];                               // F C
+#pragma unroll
+        for (int l = 1; l < NS; l++) g3 += sh(f, ga + l * NS) * Ck[l + gb * NS];
+        double g2 = Ck[ga * NS] * sh(f, gb * NS);                          // C' F
+#pragma unroll
+        for (int l = 1; l < NS; l++) g2 += Ck[l + ga * NS] * sh(f, l + gb * NS);
+        double g1 = Ck[ga * NS] * sh(g3, gb * NS);                         // C' (F C)
+#pragma unroll
+        for (int l = 1; l < NS; l++) g1 += Ck[l + ga * NS] * sh(g3, l + gb * NS);
+        if (valid) {
+            const size_t w = (size_t)ge * Nk + k;
+            P.G[w] = f; P.G[w + dof] = g1; P.G[w + 2 * (size_t)dof] = g2; P.G[w + 3 * (size_t)dof] = g3;
+        }
+    }
+    __device__ void phase_G(const double *F) {
+        for (int k0 = gwarp * KPW; k0 < P.Nk; k0 += gwarps * KPW) {
+            const int kk = k0 + lane / GW, k = min(kk, P.Nk - 1);
+            g_block(k, kk < P.Nk && gact, F[(size_t)k * NB + ge]);
+        }
+    }
+
+    // ---- (2) line sums.  Lines [0, 2Nk-1) are diagonals ip - iq = L-(Nk-1); [2Nk-1, 3Nk-2) antidiagonals iq + ip =
+    //      L-(2Nk-1).  This rank owns L = rank, rank + world, ... (line lengths vary smoothly with L, so the interleave
+    //      balances).  The work is split by species pair e = (a,b) FIRST: a block stages the four operand vectors of ITS e
+    //      (F, G1, G2, G3 along k: 32 Nk bytes) and the wavenumbers in shared memory and then walks lines reading only
+    //      shared memory -- every operand is used by ~3 Nk lines, and re-reading them from L2 per entry made the walk
+    //      L2-bandwidth bound (6 GB per evaluation at Ns=4, Nk=2000).
+    __device__ void phase_lines() {
         extern __shared__ double gsm[];
         const int Nk = P.Nk, world = P.world, rank = P.rank;
-        const int e = blockIdx.x % nb;                       // species pair of this block
-        const int chunk = blockIdx.x / nb, nchunk = (gridDim.x - e + nb - 1) / nb;    // blocks sharing this e
+        const int nlines = 3 * Nk - 2;
+        const size_t xwords = (size_t)3 * Nk * 3 * NB;
+        xepoch++;
+        const double *Fs = P.G, *G1 = P.G + dof, *G2 = P.G + 2 * (size_t)dof, *G3 = P.G + 3 * (size_t)dof;
+        const int e = blockIdx.x % NB;                       // species pair of this block
+        const int chunk = blockIdx.x / NB, nchunk = (gridDim.x - e + NB - 1) / NB;    // blocks sharing this e
         double *sF = gsm, *s1 = gsm + Nk, *s2 = gsm + 2 * Nk, *s3 = gsm + 3 * Nk, *sk = gsm + 4 * Nk;
         for (int k = threadIdx.x; k < Nk; k += blockDim.x) {
             sF[k] = Fs[(size_t)e * Nk + k]; s1[k] = G1[(size_t)e * Nk + k]; s2[k] = G2[(size_t)e * Nk + k]; s3[k] = G3[(size_t)e * Nk + k];
@@ -125,62 +234,14 @@ struct Ctx {
             }
             a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
             if (lane == 0) {
-                const size_t w = (size_t)L * 3 * nb + e;
-                if (world == 1) { P.Lsum[w] = a0; P.Lsum[w + nb] = a1; P.Lsum[w + 2 * nb] = a2; }
+                const size_t w = (size_t)L * 3 * NB + e;
+                if (world == 1) { P.Lsum[w] = a0; P.Lsum[w + NB] = a1; P.Lsum[w + 2 * NB] = a2; }
                 else for (int r = 0; r < world; r++) {
                     double *dst = P.xpeer[r] + (size_t)(xepoch & 3u) * xwords + w;
-                    st_relaxed_sys(dst, a0); st_relaxed_sys(dst + nb, a1); st_relaxed_sys(dst + 2 * nb, a2);
+                    st_relaxed_sys(dst, a0); st_relaxed_sys(dst + NB, a1); st_relaxed_sys(dst + 2 * NB, a2);
                 }
             }
         }
-        __syncthreads();
-    }
-
-    // ---- K = kernel(F)  (ends with a grid barrier; Kout valid for every thread afterwards)
-    __device__ void eval(const double *F, double *Kout) {
-        const int Nk = P.Nk, ns = P.ns;
-        if (P.type == GK_DDIM) {
-            // P[iq] = sum_{ik,ip} prefactor*J*V * F[ik]*F[ip]   (ModeCouplingKernels.jl:237-256)
-            __shared__ double red[kGT / 32];
-            for (int iq = blockIdx.x; iq < Nk; iq += gridDim.x) {
-                const double *W = P.W + (size_t)iq * Nk * Nk;
-                double s = 0.0;
-                for (int i = threadIdx.x; i < Nk * Nk; i += blockDim.x) {
-                    const int ik = i / Nk, ip = i - ik * Nk;
-                    s += W[i] * F[ik] * F[ip];
-                }
-                s = warp_sum(s);
-                if (lane == 0) red[threadIdx.x >> 5] = s;
-                __syncthreads();
-                if (threadIdx.x == 0) { double t = 0.0; for (int w = 0; w < kGT / 32; w++) t += red[w]; Kout[iq] = t; }
-                __syncthreads();
-            }
-            grid.sync();
-            return;
-        }
-        // (1) G1 = C'FC, G2 = C'F, G3 = FC per wavenumber, stored species-major ([e][k]) together with a copy of F so that
-        //     the line walk below reads unit-stride along k
-        double *Fs = P.G, *G1 = P.G + dof, *G2 = P.G + 2 * (size_t)dof, *G3 = P.G + 3 * (size_t)dof;
-        for (int k = gtid; k < Nk; k += gthreads) {
-            const double *Ck = P.C + (size_t)k * nb, *Fk = F + (size_t)k * nb;
-            double ct[kNB], g1[kNB], g2[kNB], g3[kNB];
-            for (int a = 0; a < ns; a++) for (int b = 0; b < ns; b++) ct[a + b * ns] = Ck[b + a * ns];
-            blk_mul(ns, Fk, Ck, g3);
-            blk_mul(ns, ct, Fk, g2);
-            blk_mul(ns, ct, g3, g1);
-            for (int e = 0; e < nb; e++) {
-                Fs[(size_t)e * Nk + k] = Fk[e]; G1[(size_t)e * Nk + k] = g1[e]; G2[(size_t)e * Nk + k] = g2[e]; G3[(size_t)e * Nk + k] = g3[e];
-            }
-        }
-        grid.sync();
-        // (2) line sums: lines [0, 2Nk-1) are diagonals ip - iq = L-(Nk-1); [2Nk-1, 3Nk-2) antidiagonals iq + ip = L-(2Nk-1)
-        const int nlines = 3 * Nk - 2;
-        const int world = P.world, rank = P.rank;
-        const size_t xwords = (size_t)3 * Nk * 3 * nb;
-        xepoch++;
-        double *lcur = (world > 1) ? P.xpeer[rank] + (size_t)(xepoch & 3u) * xwords : P.Lsum;
-        // this rank's lines: L = rank, rank + world, ...  (line lengths vary smoothly with L, so the interleave balances)
-        line_sums(Fs, G1, G2, G3, nlines, xwords);
         if (world > 1) {
             // re-arm this rank's own copy of the buffer used two exchanges from now (every peer wrote it two exchanges ago
             // and will write it again only after it has seen this rank's data of the next exchange)
@@ -188,53 +249,98 @@ struct Ctx {
             for (size_t i = gtid; i < xwords; i += gthreads) clr[i] = kSentinel;
             __threadfence_system();
         }
-        grid.sync();
-        // (3) bengtzelius3! (:2-43) as a prefix over the line sums: increments per ik (whole grid), then one warp per
-        //     (m, e) sequence scans its Nk increments 32 at a time; K = k T1 + T2/k^3 + T3/k   (:215-218)
-        {
-            const long long t0 = clock64();
-            // line sums of other ranks arrive through NVLink: every word validates itself (sentinel until stored)
-            auto rd = [&](size_t w) -> double {
-                if (world == 1) return lcur[w];
-                unsigned long long v;
-                unsigned spins = 0;
-                while ((v = ld_relaxed_sys_bits(lcur + w)) == kSentinel) {
-                    if ((++spins & 1023u) == 0 && clock64() - t0 > P.spin_limit_cycles) { failed = true; return 0.0; }
-                }
-                return __longlong_as_double((long long)v);
-            };
-            const int nseq = 3 * nb;
-            double *inc = P.Inc;                                   // [nseq][Nk]
-            for (size_t i = gtid; i < (size_t)nseq * Nk; i += gthreads) {
-                const int ik = (int)(i / nseq) + 1, c = (int)(i % nseq);      // consecutive threads: consecutive words of a line
-                double v = rd((size_t)((Nk - 1) + (ik - 1)) * nseq + c);
-                if (ik > 1) { v += rd((size_t)((Nk - 1) - (ik - 1)) * nseq + c); v -= rd((size_t)((2 * Nk - 1) + (ik - 2)) * nseq + c); }
-                inc[(size_t)c * Nk + (ik - 1)] = v;
+    }
+
+    // ---- (3) bengtzelius3! (:2-43) as a prefix over the line sums.  One block per (m, e) sequence: its warps take
+    //      contiguous segments, form the increments (diagonal + lower diagonal - antidiagonal) straight from the line
+    //      sums, scan them 32 at a time and add the totals of the segments before them.
+    __device__ void phase_scan() {
+        __shared__ double wtot[kGT / 32];
+        const int Nk = P.Nk, world = P.world, nseq = 3 * NB;
+        const size_t xwords = (size_t)3 * Nk * 3 * NB;
+        const double *lcur = (world > 1) ? P.xpeer[P.rank] + (size_t)(xepoch & 3u) * xwords : P.Lsum;
+        const long long t0 = clock64();
+        // line sums of other ranks arrive through NVLink: every word validates itself (sentinel until stored)
+        auto rd = [&](size_t w) -> double {
+            if (world == 1) return lcur[w];
+            unsigned long long v;
+            unsigned spins = 0;
+            while ((v = ld_relaxed_sys_bits(lcur + w)) == kSentinel) {
+                if ((++spins & 1023u) == 0 && clock64() - t0 > P.spin_limit_cycles) { failed = true; return 0.0; }
             }
-            if (failed) *P.status = MCT_CUDA_ERROR;
-        }
-        grid.sync();
-        for (int c = gwarp; c < 3 * nb; c += gwarps) {
-            const double *inc = P.Inc + (size_t)c * Nk;
+            return __longlong_as_double((long long)v);
+        };
+        const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+        const int seg = ((Nk + nw * 32 - 1) / (nw * 32)) * 32;
+        const int b0 = min(Nk, w * seg), b1 = min(Nk, b0 + seg);
+        for (int c = blockIdx.x; c < nseq; c += gridDim.x) {
             double *Tm = P.Tm + (size_t)c * Nk;
             double carry = 0.0;
-            for (int b0 = 0; b0 < Nk; b0 += 32) {
-                const int ik = b0 + lane;
-                double v = (ik < Nk) ? inc[ik] : 0.0;
+#pragma unroll 4
+            for (int i0 = b0; i0 < b1; i0 += 32) {
+                const int ik = i0 + lane;                      // 0-based; the reference's ik is this + 1
+                double v = 0.0;
+                if (ik < b1) {
+                    v = rd((size_t)((Nk - 1) + ik) * nseq + c);
+                    if (ik > 0) { v += rd((size_t)((Nk - 1) - ik) * nseq + c); v -= rd((size_t)((2 * Nk - 1) + (ik - 1)) * nseq + c); }
+                }
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) { const double u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
                 v += carry;
-                if (ik < Nk) Tm[ik] = v;
+                if (ik < b1) Tm[ik] = v;
                 carry = __shfl_sync(0xffffffffu, v, 31);
             }
+            if (lane == 0) wtot[w] = carry;
+            __syncthreads();
+            double off = 0.0;
+            for (int j = 0; j < w; j++) off += wtot[j];
+            if (w > 0) for (int ik = b0 + lane; ik < b1; ik += 32) Tm[ik] += off;     // this lane's own stores
+            __syncthreads();
+        }
+        if (failed) *P.status = MCT_CUDA_ERROR;
+    }
+    // K = k T1 + T2/k^3 + T3/k   (:215-218)
+    __device__ __forceinline__ double K_of(int ik, int e) const {
+        const double k = P.kvec[ik];
+        return k * P.Tm[(size_t)e * P.Nk + ik] + P.Tm[(size_t)(NB + e) * P.Nk + ik] / (k * k * k) + P.Tm[(size_t)(2 * NB + e) * P.Nk + ik] / k;
+    }
+
+    // P[iq] = sum_{ik,ip} prefactor*J*V * F[ik]*F[ip]   (ModeCouplingKernels.jl:237-256); ends with a grid barrier
+    __device__ void eval_ddim(const double *F, double *Kout) {
+        const int Nk = P.Nk;
+        __shared__ double red[kGT / 32];
+        for (int iq = blockIdx.x; iq < Nk; iq += gridDim.x) {
+            const double *W = P.W + (size_t)iq * Nk * Nk;
+            double s = 0.0;
+            for (int i = threadIdx.x; i < Nk * Nk; i += blockDim.x) {
+                const int ik = i / Nk, ip = i - ik * Nk;
+                s += W[i] * F[ik] * F[ip];
+            }
+            s = warp_sum(s);
+            if (lane == 0) red[threadIdx.x >> 5] = s;
+            __syncthreads();
+            if (threadIdx.x == 0) { double t = 0.0; for (int w = 0; w < kGT / 32; w++) t += red[w]; Kout[iq] = t; }
+            __syncthreads();
         }
         grid.sync();
-        for (size_t i = gtid; i < (size_t)dof; i += gthreads) {
-            const int ik = (int)(i / nb), e = (int)(i % nb);
-            const double k = P.kvec[ik];
-            Kout[i] = k * P.Tm[(size_t)e * Nk + ik] + P.Tm[(size_t)(nb + e) * Nk + ik] / (k * k * k) + P.Tm[(size_t)(2 * nb + e) * Nk + ik] / k;
-        }
+    }
+
+    // ---- K = kernel(F)  (ends with a grid barrier; Kout valid for every thread afterwards)
+    __device__ void eval(const double *F, double *Kout) {
+        if (P.type == GK_DDIM) { eval_ddim(F, Kout); return; }
+        tp = clock64();
+        phase_G(F);
         grid.sync();
+        mark(0);
+        phase_lines();
+        grid.sync();
+        mark(1);
+        phase_scan();
+        grid.sync();
+        mark(2);
+        for (size_t i = gtid; i < (size_t)dof; i += gthreads) Kout[i] = K_of((int)(i / NB), (int)(i % NB));
+        grid.sync();
+        mark(3);
     }
 
     // max |a - b| over the grid through a rotating atomic word; every thread returns the same value
@@ -255,26 +361,15 @@ struct Ctx {
         return r;
     }
 
-    // F = C1 \ (-K*C2 + C3) for every wavenumber; returns the local max |F - Fold| and sets Fold = F  (:326-337, :410-414)
-    __device__ double update_F(const double *K, double *Fdst, bool track) {
-        const int ns = P.ns;
-        double lerr = 0.0;
-        for (int k = gtid; k < P.Nk; k += gthreads) {
-            const size_t o = (size_t)k * nb;
-            double t[kNB], x[kNB];
-            blk_mul(ns, K + o, P.C2 + o, t);
-            for (int e = 0; e < nb; e++) t[e] = -t[e] + P.C3[o + e];
-            blk_solve(ns, P.C1 + o, t, x);
-            for (int e = 0; e < nb; e++) {
-                if (track) { const double d = fabs(x[e] - P.Fold[o + e]); if (d > lerr) lerr = d; P.Fold[o + e] = x[e]; }
-                Fdst[o + e] = x[e];
-            }
-        }
-        return lerr;
+    // this lane's element of F = C1 \ (-K*C2 + C3) at block offset o; K spread over the group  (:326-337)
+    __device__ __forceinline__ double update_group(size_t o, double Kreg) const {
+        double t = mm_rg(Kreg, P.C2 + o);
+        t = -t + P.C3[o + ge];
+        return solve_group(P.C1 + o, t);
     }
 
     __device__ void run() {
-        const int Nk = P.Nk, ns = P.ns, N = P.N, n4 = 4 * N, n2 = 2 * N;
+        const int Nk = P.Nk, N = P.N, n4 = 4 * N, n2 = 2 * N;
         unsigned ecount = 0;
 #define FT(s) (P.Ft + (size_t)dof * ((s) - 1))
 #define KT(s) (P.Kt + (size_t)dof * ((s) - 1))
@@ -294,12 +389,12 @@ struct Ctx {
                 if (iter > P.max_iter) { status = MCT_NOT_CONVERGED; break; }
                 double lerr = 0.0;
                 for (int k = gtid; k < Nk; k += gthreads) {
-                    const size_t o = (size_t)k * nb;
-                    double t[kNB], M[kNB], x[kNB];
-                    blk_mul(ns, P.Kcur + o, P.F0 + o, t);                                  // :81
-                    for (int e = 0; e < nb; e++) M[e] = P.Kcur[o + e] + P.gamma[o + e];    // :83
-                    blk_solve(ns, M, t, x);
-                    for (int e = 0; e < nb; e++) { const double d = fabs(x[e] - P.Fold[o + e]); if (d > lerr) lerr = d; P.Fold[o + e] = x[e]; P.Fcur[o + e] = x[e]; }
+                    const size_t o = (size_t)k * NB;
+                    double t[NB], M[NB], x[NB];
+                    blk_mul<NS>(P.Kcur + o, P.F0 + o, t);                                  // :81
+                    for (int e = 0; e < NB; e++) M[e] = P.Kcur[o + e] + P.gamma[o + e];    // :83
+                    blk_solve<NS, NS>(M, t, x);
+                    for (int e = 0; e < NB; e++) { const double d = fabs(x[e] - P.Fold[o + e]); if (d > lerr) lerr = d; P.Fold[o + e] = x[e]; P.Fcur[o + e] = x[e]; }
                 }
                 const double err = grid_max(lerr, ecount);
                 eval(P.Fcur, P.Kcur);                                                      // :89
@@ -310,7 +405,7 @@ struct Ctx {
             return;
         }
         // ---- time doubling.  F_old = K0*F0 (:64); K_temp slots keep 2 K0 until they are evaluated (:83)
-        for (int k = gtid; k < Nk; k += gthreads) blk_mul(ns, P.K0 + (size_t)k * nb, P.F0 + (size_t)k * nb, P.Fold + (size_t)k * nb);
+        for (int k = gtid; k < Nk; k += gthreads) blk_mul<NS>(P.K0 + (size_t)k * NB, P.F0 + (size_t)k * NB, P.Fold + (size_t)k * NB);
         for (int e = gtid; e < dof; e += gthreads) {
             for (int s = n2 + 1; s <= n4; s++) KT(s)[e] = P.K0[e] + P.K0[e];
             P.dFh[e] = P.dF0[e];
@@ -321,42 +416,42 @@ struct Ctx {
         const double de = P.dt0 / (4.0 * N);
         for (int it = 1; it <= n2; it++) {
             for (int k = gtid; k < Nk; k += gthreads) {
-                const size_t o = (size_t)k * nb;
-                double integ[kNB], f[kNB];
+                const size_t o = (size_t)k * NB;
+                double integ[NB], f[NB];
                 // integrand[i] = K_array[i] * dF_reverse[i] = K(t_{i-1}) * dF(t_{it-i}), i = 1..it
                 if (it == 1) {
-                    blk_mul(ns, P.K0 + o, P.dFh + o, f);
-                    for (int e = 0; e < nb; e++) integ[e] = f[e] * de;                     // :34-36
+                    blk_mul<NS>(P.K0 + o, P.dFh + o, f);
+                    for (int e = 0; e < NB; e++) integ[e] = f[e] * de;                     // :34-36
                 } else {
-                    double r[kNB];
-                    blk_mul(ns, P.K0 + o, P.dFh + (size_t)dof * (it - 1) + o, f);
-                    for (int e = 0; e < nb; e++) r[e] = f[e] / 2.0;
-                    blk_mul(ns, KT(it - 1) + o, P.dFh + o, f);
-                    for (int e = 0; e < nb; e++) r[e] += f[e] / 2.0;
+                    double r[NB];
+                    blk_mul<NS>(P.K0 + o, P.dFh + (size_t)dof * (it - 1) + o, f);
+                    for (int e = 0; e < NB; e++) r[e] = f[e] / 2.0;
+                    blk_mul<NS>(KT(it - 1) + o, P.dFh + o, f);
+                    for (int e = 0; e < NB; e++) r[e] += f[e] / 2.0;
                     for (int i = 2; i <= it - 1; i++) {
-                        blk_mul(ns, KT(i - 1) + o, P.dFh + (size_t)dof * (it - i) + o, f);
-                        for (int e = 0; e < nb; e++) r[e] += f[e];
+                        blk_mul<NS>(KT(i - 1) + o, P.dFh + (size_t)dof * (it - i) + o, f);
+                        for (int e = 0; e < NB; e++) r[e] += f[e];
                     }
-                    for (int e = 0; e < nb; e++) integ[e] = r[e] * de;
+                    for (int e = 0; e < NB; e++) integ[e] = r[e] * de;
                 }
                 const double *Fo = (it == 1) ? P.F0 + o : FT(it - 1) + o;
                 const double *dFo = P.dFh + (size_t)dof * (it - 1) + o;
-                double gF[kNB], rhs[kNB], neg[kNB], sol[kNB];
-                blk_mul(ns, P.gamma + o, Fo, gF);
+                double gF[NB], rhs[NB], neg[NB], sol[NB];
+                blk_mul<NS>(P.gamma + o, Fo, gF);
                 if (P.second_order) {                                                      // Euler_step :55-58
-                    double bdF[kNB];
-                    blk_mul(ns, P.beta + o, dFo, bdF);
-                    for (int e = 0; e < nb; e++) { rhs[e] = bdF[e] + gF[e] + P.delta[o + e] + integ[e]; neg[e] = -P.alpha[o + e]; }
-                    blk_solve(ns, neg, rhs, sol);
-                    for (int e = 0; e < nb; e++) {
+                    double bdF[NB];
+                    blk_mul<NS>(P.beta + o, dFo, bdF);
+                    for (int e = 0; e < NB; e++) { rhs[e] = bdF[e] + gF[e] + P.delta[o + e] + integ[e]; neg[e] = -P.alpha[o + e]; }
+                    blk_solve<NS, NS>(neg, rhs, sol);
+                    for (int e = 0; e < NB; e++) {
                         const double dFn = dFo[e] + de * sol[e];
                         P.dFh[(size_t)dof * it + o + e] = dFn;
                         FT(it)[o + e] = Fo[e] + de * dFn;
                     }
                 } else {                                                                   // :60-61
-                    for (int e = 0; e < nb; e++) { rhs[e] = gF[e] + P.delta[o + e] + integ[e]; neg[e] = -P.beta[o + e]; }
-                    blk_solve(ns, neg, rhs, sol);
-                    for (int e = 0; e < nb; e++) {
+                    for (int e = 0; e < NB; e++) { rhs[e] = gF[e] + P.delta[o + e] + integ[e]; neg[e] = -P.beta[o + e]; }
+                    blk_solve<NS, NS>(neg, rhs, sol);
+                    for (int e = 0; e < NB; e++) {
                         P.dFh[(size_t)dof * it + o + e] = sol[e];
                         FT(it)[o + e] = Fo[e] + de * sol[e];
                     }
@@ -376,6 +471,7 @@ struct Ctx {
             }
         }
         grid.sync();
+        const bool mc = P.type == GK_MC3D;
         long long evals = 0;
         int status = MCT_OK;
         double Dt = P.dt0;
@@ -384,43 +480,72 @@ struct Ctx {
             for (int it = n2 + 1; it <= n4 && status == MCT_OK; it++) {
                 const int i2 = it / 2;
                 const long long row = 1 + (long long)n2 * (blk + 1) + (it - n2 - 1);
+                tp = clock64();
                 // update_Fuchs_parameters! :300-319 (compute_C3_mutable! :243-288), then update_F! with the stale K_temp[it]
-                for (int k = gtid; k < Nk; k += gthreads) {
-                    const size_t o = (size_t)k * nb;
-                    double tv[kNB], c3[kNB], t[kNB], u[kNB];
-                    for (int e = 0; e < nb; e++)
-                        P.C1[o + e] = ((2.0 / (dl * dl) * P.alpha[o + e] + 3.0 / (2.0 * dl) * P.beta[o + e]) + KINT(1)[o + e]) + P.gamma[o + e];   // :314
-                    for (int e = 0; e < nb; e++) P.C2[o + e] = FINT(1)[o + e] - P.F0[o + e];                                                        // :315
-                    for (int e = 0; e < nb; e++) tv[e] = (5.0 * FT(it - 1)[o + e] - 4.0 * FT(it - 2)[o + e] + FT(it - 3)[o + e]) / (dl * dl);
-                    blk_mul(ns, P.alpha + o, tv, c3);                                                                                              // :259-260
-                    for (int e = 0; e < nb; e++) tv[e] = 2.0 / dl * FT(it - 1)[o + e] - FT(it - 2)[o + e] / (2.0 * dl);
-                    blk_mul(ns, P.beta + o, tv, t);
-                    for (int e = 0; e < nb; e++) c3[e] += t[e];                                                                                    // :263-264
-                    blk_mul(ns, KT(it - i2) + o, FT(i2) + o, t); for (int e = 0; e < nb; e++) c3[e] -= t[e];                                        // :267
-                    blk_mul(ns, KT(it - 1) + o, FINT(1) + o, t); for (int e = 0; e < nb; e++) c3[e] += t[e];                                        // :268
-                    blk_mul(ns, KINT(1) + o, FT(it - 1) + o, t); for (int e = 0; e < nb; e++) c3[e] += t[e];                                        // :269
-                    for (int j = 2; j <= i2; j++) {                                                                                                // :271-280
-                        for (int e = 0; e < nb; e++) u[e] = KT(it - j)[o + e] - KT(it - j + 1)[o + e];
-                        blk_mul(ns, u, FINT(j) + o, t);
-                        for (int e = 0; e < nb; e++) c3[e] += t[e];
+                // and the G matrices of the first evaluation, all on the lanes of the wavenumber's group
+                for (int k0 = gwarp * KPW; k0 < Nk; k0 += gwarps * KPW) {
+                    const int kk = k0 + lane / GW, k = min(kk, Nk - 1);
+                    const bool valid = kk < Nk && gact;
+                    const size_t o = (size_t)k * NB, oe = o + ge;
+                    const double c1 = ((2.0 / (dl * dl) * P.alpha[oe] + 3.0 / (2.0 * dl) * P.beta[oe]) + KINT(1)[oe]) + P.gamma[oe];   // :314
+                    const double c2 = FINT(1)[oe] - P.F0[oe];                                                                            // :315
+                    double tv = (5.0 * FT(it - 1)[oe] - 4.0 * FT(it - 2)[oe] + FT(it - 3)[oe]) / (dl * dl);
+                    double c3 = mm_gr(P.alpha + o, tv);                                                                                  // :259-260
+                    tv = 2.0 / dl * FT(it - 1)[oe] - FT(it - 2)[oe] / (2.0 * dl);
+                    c3 += mm_gr(P.beta + o, tv);                                                                                         // :263-264
+                    c3 -= mm_gg(KT(it - i2) + o, FT(i2) + o);                                                                            // :267
+                    c3 += mm_gg(KT(it - 1) + o, FINT(1) + o);                                                                            // :268
+                    c3 += mm_gg(KINT(1) + o, FT(it - 1) + o);                                                                            // :269
+#pragma unroll 2
+                    for (int j = 2; j <= i2; j++) {                                                                                      // :271-280
+                        const double *Ka = KT(it - j) + o, *Kb = KT(it - j + 1) + o, *Fi = FINT(j) + o;
+                        double t = (Ka[ga] - Kb[ga]) * Fi[gb * NS];
+#pragma unroll
+                        for (int l = 1; l < NS; l++) t += (Ka[ga + l * NS] - Kb[ga + l * NS]) * Fi[l + gb * NS];
+                        c3 += t;
                     }
-                    for (int j = 2; j <= it - i2; j++) {                                                                                           // :281-285
-                        for (int e = 0; e < nb; e++) u[e] = FT(it - j)[o + e] - FT(it - j + 1)[o + e];
-                        blk_mul(ns, KINT(j) + o, u, t);
-                        for (int e = 0; e < nb; e++) c3[e] += t[e];
+#pragma unroll 2
+                    for (int j = 2; j <= it - i2; j++) {                                                                                 // :281-285
+                        const double *Ki = KINT(j) + o, *Fa = FT(it - j) + o, *Fb = FT(it - j + 1) + o;
+                        double t = Ki[ga] * (Fa[gb * NS] - Fb[gb * NS]);
+#pragma unroll
+                        for (int l = 1; l < NS; l++) t += Ki[ga + l * NS] * (Fa[l + gb * NS] - Fb[l + gb * NS]);
+                        c3 += t;
                     }
-                    for (int e = 0; e < nb; e++) P.C3[o + e] = c3[e] - P.delta[o + e];                                                             // :286
+                    c3 -= P.delta[oe];                                                                                                   // :286
+                    const double Kst = KT(it)[oe];
+                    if (valid) { P.C1[oe] = c1; P.C2[oe] = c2; P.C3[oe] = c3; }
+                    __syncwarp();
+                    const double x = update_group(o, Kst);
+                    if (valid) FT(it)[oe] = x;
+                    if (mc) g_block(k, valid, x);
                 }
-                // the same thread owns wavenumber k in every per-k phase: no barrier needed between them
-                update_F(KT(it), FT(it), false);
                 grid.sync();
+                mark(4);
                 long long iter = 0;
                 while (true) {
                     iter++;
                     if (iter > P.max_iter) { status = MCT_NOT_CONVERGED; break; }          // :406-408
-                    eval(FT(it), KT(it));                                                  // update_K! :360-369
-                    const double lerr = update_F(KT(it), FT(it), true);                    // update_F! + find_error + F_old .= F
+                    // update_K! :360-369
+                    if (mc) { phase_lines(); grid.sync(); mark(1); phase_scan(); grid.sync(); mark(2); }
+                    else eval_ddim(FT(it), KT(it));
+                    // K from the prefix sums, update_F! + find_error + F_old .= F, and the G matrices of the next evaluation
+                    double lerr = 0.0;
+                    for (int k0 = gwarp * KPW; k0 < Nk; k0 += gwarps * KPW) {
+                        const int kk = k0 + lane / GW, k = min(kk, Nk - 1);
+                        const bool valid = kk < Nk && gact;
+                        const size_t o = (size_t)k * NB, oe = o + ge;
+                        const double Kv = mc ? K_of(k, ge) : KT(it)[oe];
+                        const double x = update_group(o, Kv);
+                        if (valid) {
+                            const double d = fabs(x - P.Fold[oe]); if (d > lerr) lerr = d;
+                            P.Fold[oe] = x; FT(it)[oe] = x;
+                            if (mc) KT(it)[oe] = Kv;
+                        }
+                        if (mc) g_block(k, valid, x);
+                    }
                     const double err = grid_max(lerr, ecount);
+                    mark(5);
                     evals++;                                                               // :416
                     if (!(err > P.tol)) break;
                 }
@@ -452,8 +577,9 @@ struct Ctx {
     }
 };
 
+template <int NS>
 __global__ void __launch_bounds__(kGT) td_grid_kernel(const GridParams P) {
-    Ctx c(P);
+    Ctx<NS> c(P);
     c.run();
 }
 
@@ -478,16 +604,18 @@ int ddim_build_table(int Nk, double prefactor, const double *dV, const double *d
 
 int td_grid_launch(const GridParams &P, int n_sm, cudaStream_t stream) {
     MCT_REQUIRE(P.ns >= 1 && P.ns <= kNsMax, MCT_UNSUPPORTED, "Ns > 4 is not supported on the device");
-    // multi-component: five vectors of Nk doubles per block in shared memory (line_sums)
+    const void *fn = P.ns == 1 ? (const void *)td_grid_kernel<1> : P.ns == 2 ? (const void *)td_grid_kernel<2>
+                   : P.ns == 3 ? (const void *)td_grid_kernel<3> : (const void *)td_grid_kernel<4>;
+    // multi-component: five vectors of Nk doubles per block in shared memory (phase_lines)
     const size_t smem = (P.type == GK_MC3D) ? (size_t)5 * P.Nk * sizeof(double) : 0;
-    MCT_CUDA(cudaFuncSetAttribute((void *)td_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MCT_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    MCT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, td_grid_kernel, kGT, smem));
+    MCT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kGT, smem));
     MCT_REQUIRE(per_sm >= 1, MCT_CUDA_ERROR, "cooperative kernel does not fit");
     GridParams Pc = P;
     void *args[] = {(void *)&Pc};
     dim3 grid(n_sm * std::min(per_sm, 2)), block(kGT);
-    MCT_CUDA(cudaLaunchCooperativeKernel((void *)td_grid_kernel, grid, block, args, smem, stream));
+    MCT_CUDA(cudaLaunchCooperativeKernel(fn, grid, block, args, smem, stream));
     count_launch();
     return MCT_OK;
 }

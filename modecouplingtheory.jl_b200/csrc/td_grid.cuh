@@ -38,6 +38,7 @@ struct GridParams {
     long long spin_limit_cycles;
     int *status;
     long long *kernel_evals;
+    unsigned long long *prof;    // [12] cycles per phase seen by thread 0 (diagnostics, printed with MCT_GRID_PROF=1)
 };
 
 int td_grid_launch(const GridParams &P, int n_sm, cudaStream_t stream);
