@@ -461,7 +461,7 @@ static int grid_setup(mct_equation_t q, mct_kernel_t h, int mode, const std::vec
     const int N = (mode == 0) ? q->opts.N : 1;
     const size_t ring = (mode == 0) ? (size_t)4 * N * dof : 0;
     const size_t traj = (mode == 0) ? (size_t)q->nt * dof : dof;
-    const size_t lsum = (size_t)3 * Nk * 3 * nb;
+    const size_t lsum = grid_lsum_words(Nk, ns);
     const size_t dfh = (mode == 0) ? (size_t)(2 * N + 1) * dof : 0;
     const size_t total = 6 * dof + 4 * ring + 7 * dof + 4 * dof + 6 * dof + lsum + dfh + 2 * traj + 40;
     MCT_CUDA(cudaMalloc(&q->d_gws, total * sizeof(double)));
@@ -870,7 +870,7 @@ int mct_equation_shard_prepare(mct_equation_t q, int rank, int world, unsigned c
     MCT_REQUIRE(q->kernel && q->kernel->type == K_MC3D, MCT_UNSUPPORTED, "k-sharding is implemented for the multi-component kernel");
     MCT_REQUIRE(world >= 2 && world <= kMaxShardRanks && rank >= 0 && rank < world, MCT_BAD_ARGUMENT, "bad rank / world size (2..8)");
     MCT_CUDA(cudaSetDevice(q->kernel->device));
-    const size_t xwords = (size_t)3 * q->Nk * 3 * q->ns * q->ns;
+    const size_t xwords = grid_lsum_words(q->Nk, q->ns);
     if (!q->d_xshard) MCT_CUDA(cudaMalloc(&q->d_xshard, 4 * xwords * sizeof(double)));
     MCT_CUDA(cudaMemset(q->d_xshard, 0xFF, 4 * xwords * sizeof(double)));          // every slot armed with the sentinel
     cudaIpcMemHandle_t hd;

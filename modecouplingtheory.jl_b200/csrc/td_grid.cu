@@ -193,53 +193,115 @@ struct Ctx {
         }
     }
 
-    // ---- (2) line sums.  Lines [0, 2Nk-1) are diagonals ip - iq = L-(Nk-1); [2Nk-1, 3Nk-2) antidiagonals iq + ip =
-    //      L-(2Nk-1).  This rank owns L = rank, rank + world, ... (line lengths vary smoothly with L, so the interleave
-    //      balances).  The work is split by species pair e = (a,b) FIRST: a block stages the four operand vectors of ITS e
-    //      (F, G1, G2, G3 along k: 32 Nk bytes) and the wavenumbers in shared memory and then walks lines reading only
-    //      shared memory -- every operand is used by ~3 Nk lines, and re-reading them from L2 per entry made the walk
-    //      L2-bandwidth bound (6 GB per evaluation at Ns=4, Nk=2000).
+    // ---- (2) line sums of A_m[a,b,iq,ip] along the diagonals d = ip - iq and the antidiagonals s = iq + ip <= Nk-2 that
+    //      bengtzelius3! (:2-43) walks.  The work is split by species pair e = (a,b) FIRST: a block stages the four operand
+    //      vectors of ITS e (F, G1, G2, G3 along k) and the wavenumbers in shared memory (zero padded to a multiple of 4).
+    //      The (iq, ip) plane is cut into 4 x 4 tiles; a warp task is one tile diagonal (J - I = D >= 0: lines 4D-3 .. 4D+3)
+    //      or tile antidiagonal (I + J = S: lines 4S .. 4S+6), its lanes stride over the tiles of the task.  Only d >= 0
+    //      is walked: for a fixed species pair the entry at (ip, iq) equals the one at (iq, ip) (t1 <-> t4, t2 <-> t3 and
+    //      the sign of p^2 - q^2 swap together), so the line sums of d and -d are the same number.  A lane keeps
+    //      the 2 x 4 x 5 operands of a tile and 3 x 7 line accumulators in registers: 2.5 shared-memory words and 16
+    //      FP64 operations per entry (10 and 28 when every entry is walked on its own), which is what bounds this phase.
+    //      The 21 partial sums of a task are written per task; phase_scan adds the (at most two) tasks of a line.
+    //      Tasks are dealt to warps longest first in snake order; rank r of a k-sharded solve takes every world-th task.
+    template <bool DIAG>
+    __device__ __forceinline__ void tile_walk(const double *sm, int nc, int lo, int hi, int off, double (&acc)[3][8]) {
+        const double *sF = sm, *s1 = sm + 4 * nc, *s2 = sm + 8 * nc, *s3 = sm + 12 * nc, *sk = sm + 16 * nc;
+        auto ld4 = [](const double *p, double (&v)[4]) {
+            const double2 u = *reinterpret_cast<const double2 *>(p), w = *reinterpret_cast<const double2 *>(p + 2);
+            v[0] = u.x; v[1] = u.y; v[2] = w.x; v[3] = w.y;
+        };
+        for (int I = lo + lane; I < hi; I += 32) {
+            const int J = DIAG ? I + off : off - I;
+            double xF[4], x1[4], x2[4], x3[4], xk[4], yF[4], y1[4], y2[4], y3[4], yk[4], xq[4], yp[4];
+            ld4(sF + 4 * I, xF); ld4(s1 + 4 * I, x1); ld4(s2 + 4 * I, x2); ld4(s3 + 4 * I, x3); ld4(sk + 4 * I, xk);
+            ld4(sF + 4 * J, yF); ld4(s1 + 4 * J, y1); ld4(s2 + 4 * J, y2); ld4(s3 + 4 * J, y3); ld4(sk + 4 * J, yk);
+#pragma unroll
+            for (int i = 0; i < 4; i++) { xq[i] = xk[i] * xk[i]; yp[i] = yk[i] * yk[i]; }
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    const int idx = DIAG ? b - a + 3 : a + b;
+                    const double pq2 = yp[b] - xq[a], P1 = yk[b] * xk[a], w = P1 * pq2, P2 = w * pq2;   // p = k[ip], q = k[iq]
+                    const double t1 = xF[a] * y1[b], t2 = y2[b] * x3[a], t3 = x2[a] * y3[b], t4 = x1[a] * yF[b];
+                    const double v = t1 + t4, u = t2 + t3;
+                    acc[0][idx] = fma(v + u, P1, acc[0][idx]);       // :186-192 (V1: pq, V2: pq(p^2-q^2)^2, V3: 2pq(p^2-q^2))
+                    acc[1][idx] = fma(v - u, P2, acc[1][idx]);
+                    acc[2][idx] = fma(t1 - t4, w, acc[2][idx]);
+                }
+        }
+    }
     __device__ void phase_lines() {
         extern __shared__ double gsm[];
         const int Nk = P.Nk, world = P.world, rank = P.rank;
-        const int nlines = 3 * Nk - 2;
-        const size_t xwords = (size_t)3 * Nk * 3 * NB;
+        const int nc = grid_chunks(Nk), nanti = grid_anti_tasks(Nk);
+        const size_t xwords = grid_lsum_words(Nk, NS);
         xepoch++;
-        const double *Fs = P.G, *G1 = P.G + dof, *G2 = P.G + 2 * (size_t)dof, *G3 = P.G + 3 * (size_t)dof;
         const int e = blockIdx.x % NB;                       // species pair of this block
         const int chunk = blockIdx.x / NB, nchunk = (gridDim.x - e + NB - 1) / NB;    // blocks sharing this e
-        double *sF = gsm, *s1 = gsm + Nk, *s2 = gsm + 2 * Nk, *s3 = gsm + 3 * Nk, *sk = gsm + 4 * Nk;
-        for (int k = threadIdx.x; k < Nk; k += blockDim.x) {
-            sF[k] = Fs[(size_t)e * Nk + k]; s1[k] = G1[(size_t)e * Nk + k]; s2[k] = G2[(size_t)e * Nk + k]; s3[k] = G3[(size_t)e * Nk + k];
-            sk[k] = P.kvec[k];
+        for (int i = threadIdx.x; i < 4 * nc; i += blockDim.x) {
+            const bool in = i < Nk;
+#pragma unroll
+            for (int j = 0; j < 4; j++) gsm[j * 4 * nc + i] = in ? P.G[(size_t)j * dof + (size_t)e * Nk + i] : 0.0;
+            gsm[16 * nc + i] = in ? P.kvec[i] : 0.0;
         }
         __syncthreads();
         const double pab = P.pref[e];
-        const int warps_per_block = blockDim.x >> 5, wi = chunk * warps_per_block + (threadIdx.x >> 5), wstride = nchunk * warps_per_block;
-        for (int Li = wi; Li * world + rank < nlines; Li += wstride) {
-            const int L = Li * world + rank;
-            double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-            const bool diag = L < 2 * Nk - 1;
-            const int d = L - (Nk - 1), s = L - (2 * Nk - 1);
-            const int q0 = diag ? max(0, -d) : 0, q1 = diag ? min(Nk, Nk - d) : s + 1;
-            for (int iq = q0 + lane; iq < q1; iq += 32) {
-                const int ip = diag ? iq + d : s - iq;
-                const double q = sk[iq], p = sk[ip];
-                const double pq2 = p * p - q * q;
-                const double P1 = p * q, P2 = p * q * (pq2 * pq2), P3 = 2.0 * p * q * pq2;
-                const double t1 = sF[iq] * s1[ip], t2 = s2[ip] * s3[iq], t3 = s2[iq] * s3[ip], t4 = s1[iq] * sF[ip];
-                a0 += (t1 + t2 + t3 + t4) * P1 * pab;      // :186-192
-                a1 += (t1 - t2 - t3 + t4) * P2 * pab;
-                a2 += (t1 - t4) * P3 * pab;
-            }
-            a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
-            if (lane == 0) {
-                const size_t w = (size_t)L * 3 * NB + e;
-                if (world == 1) { P.Lsum[w] = a0; P.Lsum[w + NB] = a1; P.Lsum[w + 2 * NB] = a2; }
-                else for (int r = 0; r < world; r++) {
-                    double *dst = P.xpeer[r] + (size_t)(xepoch & 3u) * xwords + w;
-                    st_relaxed_sys(dst, a0); st_relaxed_sys(dst + NB, a1); st_relaxed_sys(dst + 2 * NB, a2);
+        const int wpb = blockDim.x >> 5, wi = chunk * wpb + (threadIdx.x >> 5), wstride = nchunk * wpb;
+        for (int round = 0;; round++) {
+            const int slot = round * wstride + ((round & 1) ? wstride - 1 - wi : wi);
+            const int t = slot * world + rank;               // position in the longest-first order
+            if (round * wstride * world >= 2 * nc) break;
+            if (t >= 2 * nc) continue;
+            const int lam = t >> 1, kind = t & 1;            // task length nc - lam; kind 0: D = lam, 1: S = nc-lam-1
+            if (kind == 1 && nc - lam - 1 >= nanti) continue;
+            double acc[3][8];
+#pragma unroll
+            for (int m = 0; m < 3; m++)
+#pragma unroll
+                for (int i = 0; i < 8; i++) acc[m][i] = 0.0;
+            int task;
+            if (kind == 1) { const int S = nc - lam - 1; task = nc + S; tile_walk<false>(gsm, nc, 0, S + 1, S, acc); }
+            else { task = lam; tile_walk<true>(gsm, nc, 0, nc - lam, lam, acc); }
+            // 24 values (3 x 7 used) summed over the 32 lanes by halving: lanes exchange the half they do not keep
+            double v12[12], v6[6], v4[4], v2[2];
+            {
+                const bool up = lane & 16;
+#pragma unroll
+                for (int i = 0; i < 12; i++) {
+                    const double lo = acc[i / 8][i % 8], hi = acc[(i + 12) / 8][(i + 12) % 8];
+                    const double got = __shfl_xor_sync(0xffffffffu, up ? lo : hi, 16);
+                    v12[i] = (up ? hi : lo) + got;
                 }
+            }
+            {
+                const bool up = lane & 8;
+#pragma unroll
+                for (int i = 0; i < 6; i++) { const double got = __shfl_xor_sync(0xffffffffu, up ? v12[i] : v12[i + 6], 8); v6[i] = (up ? v12[i + 6] : v12[i]) + got; }
+            }
+            {
+                const bool up = lane & 4;
+#pragma unroll
+                for (int i = 0; i < 3; i++) { const double got = __shfl_xor_sync(0xffffffffu, up ? v6[i] : v6[i + 3], 4); v4[i] = (up ? v6[i + 3] : v6[i]) + got; }
+                v4[3] = 0.0;
+            }
+            {
+                const bool up = lane & 2;
+#pragma unroll
+                for (int i = 0; i < 2; i++) { const double got = __shfl_xor_sync(0xffffffffu, up ? v4[i] : v4[i + 2], 2); v2[i] = (up ? v4[i + 2] : v4[i]) + got; }
+            }
+            const bool up1 = lane & 1;
+            double tot = (up1 ? v2[1] : v2[0]) + __shfl_xor_sync(0xffffffffu, up1 ? v2[0] : v2[1], 1);
+            // this lane now holds value number vi of the flattened [3][8] accumulators
+            const int sub = (lane & 2 ? 2 : 0) + (lane & 1);
+            const int vi = (lane & 16 ? 12 : 0) + (lane & 8 ? 6 : 0) + (lane & 4 ? 3 : 0) + sub;
+            const int m = vi >> 3, idx = vi & 7;
+            if (sub < 3 && m < 3 && idx < 7) {
+                tot *= (m == 2) ? 2.0 * pab : pab;
+                const size_t w = ((size_t)task * 7 + idx) * 3 * NB + m * NB + e;
+                if (world == 1) P.Lsum[w] = tot;
+                else for (int r = 0; r < world; r++) st_relaxed_sys(P.xpeer[r] + (size_t)(xepoch & 3u) * xwords + w, tot);
             }
         }
         if (world > 1) {
@@ -252,12 +314,13 @@ struct Ctx {
     }
 
     // ---- (3) bengtzelius3! (:2-43) as a prefix over the line sums.  One block per (m, e) sequence: its warps take
-    //      contiguous segments, form the increments (diagonal + lower diagonal - antidiagonal) straight from the line
+    //      contiguous segments, form the increments (diagonal + lower diagonal - antidiagonal) straight from the task
     //      sums, scan them 32 at a time and add the totals of the segments before them.
     __device__ void phase_scan() {
         __shared__ double wtot[kGT / 32];
         const int Nk = P.Nk, world = P.world, nseq = 3 * NB;
-        const size_t xwords = (size_t)3 * Nk * 3 * NB;
+        const int nc = grid_chunks(Nk);
+        const size_t xwords = grid_lsum_words(Nk, NS);
         const double *lcur = (world > 1) ? P.xpeer[P.rank] + (size_t)(xepoch & 3u) * xwords : P.Lsum;
         const long long t0 = clock64();
         // line sums of other ranks arrive through NVLink: every word validates itself (sentinel until stored)
@@ -270,31 +333,63 @@ struct Ctx {
             }
             return __longlong_as_double((long long)v);
         };
+        // A line collects the entries of at most two tasks.  Increment of row ik (0-based): diagonal ik + diagonal -ik
+        // (the same number, see phase_lines) - antidiagonal ik-1; ik = 0: the main diagonal alone.  Word addresses are
+        // clamped and the values selected afterwards so that the loads of a lane are independent of each other.
+        auto increment = [&](int ik, int c) -> double {
+            const int D0 = ik >> 2, r = ik & 3;
+            const bool two_d = r > 0 && D0 + 1 <= nc - 1;
+            const size_t wd0 = ((size_t)D0 * 7 + r + 3) * nseq + c, wd1 = ((size_t)(two_d ? D0 + 1 : D0) * 7 + (two_d ? r - 1 : r + 3)) * nseq + c;
+            const int s_ = max(ik - 1, 0), S0 = s_ >> 2, q = s_ & 3;
+            const bool two_a = q <= 2 && S0 >= 1;
+            const size_t wa0 = ((size_t)(nc + S0) * 7 + q) * nseq + c, wa1 = ((size_t)(nc + (two_a ? S0 - 1 : S0)) * 7 + (two_a ? q + 4 : q)) * nseq + c;
+            double d0, d1, a0, a1;
+            if (world == 1) { d0 = lcur[wd0]; d1 = lcur[wd1]; a0 = lcur[wa0]; a1 = lcur[wa1]; }
+            else { d0 = rd(wd0); d1 = two_d ? rd(wd1) : 0.0; a0 = ik > 0 ? rd(wa0) : 0.0; a1 = (ik > 0 && two_a) ? rd(wa1) : 0.0; }
+            double d = d0; if (two_d) d += d1;
+            double a = a0; if (two_a) a += a1;
+            return ik > 0 ? (d + d) - a : d;
+        };
         const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
         const int seg = ((Nk + nw * 32 - 1) / (nw * 32)) * 32;
         const int b0 = min(Nk, w * seg), b1 = min(Nk, b0 + seg);
+        constexpr int kFast = 8;                               // segments of up to 8 x 32 rows stay in registers
         for (int c = blockIdx.x; c < nseq; c += gridDim.x) {
             double *Tm = P.Tm + (size_t)c * Nk;
             double carry = 0.0;
-#pragma unroll 4
-            for (int i0 = b0; i0 < b1; i0 += 32) {
-                const int ik = i0 + lane;                      // 0-based; the reference's ik is this + 1
-                double v = 0.0;
-                if (ik < b1) {
-                    v = rd((size_t)((Nk - 1) + ik) * nseq + c);
-                    if (ik > 0) { v += rd((size_t)((Nk - 1) - ik) * nseq + c); v -= rd((size_t)((2 * Nk - 1) + (ik - 1)) * nseq + c); }
-                }
+            if (seg <= 32 * kFast) {
+                double v[kFast];
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const double u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
-                v += carry;
-                if (ik < b1) Tm[ik] = v;
-                carry = __shfl_sync(0xffffffffu, v, 31);
+                for (int j = 0; j < kFast; j++) { const int ik = b0 + 32 * j + lane; v[j] = (ik < b1) ? increment(ik, c) : 0.0; }
+#pragma unroll
+                for (int j = 0; j < kFast; j++) {
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { const double u = __shfl_up_sync(0xffffffffu, v[j], o); if (lane >= o) v[j] += u; }
+                    v[j] += carry;
+                    carry = __shfl_sync(0xffffffffu, v[j], 31);
+                }
+                if (lane == 0) wtot[w] = carry;
+                __syncthreads();
+                double off = 0.0;
+                for (int j = 0; j < w; j++) off += wtot[j];
+#pragma unroll
+                for (int j = 0; j < kFast; j++) { const int ik = b0 + 32 * j + lane; if (ik < b1) Tm[ik] = v[j] + off; }
+            } else {
+                for (int i0 = b0; i0 < b1; i0 += 32) {
+                    const int ik = i0 + lane;
+                    double v = (ik < b1) ? increment(ik, c) : 0.0;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { const double u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
+                    v += carry;
+                    if (ik < b1) Tm[ik] = v;
+                    carry = __shfl_sync(0xffffffffu, v, 31);
+                }
+                if (lane == 0) wtot[w] = carry;
+                __syncthreads();
+                double off = 0.0;
+                for (int j = 0; j < w; j++) off += wtot[j];
+                if (w > 0) for (int ik = b0 + lane; ik < b1; ik += 32) Tm[ik] += off;     // this lane's own stores
             }
-            if (lane == 0) wtot[w] = carry;
-            __syncthreads();
-            double off = 0.0;
-            for (int j = 0; j < w; j++) off += wtot[j];
-            if (w > 0) for (int ik = b0 + lane; ik < b1; ik += 32) Tm[ik] += off;     // this lane's own stores
             __syncthreads();
         }
         if (failed) *P.status = MCT_CUDA_ERROR;
@@ -578,7 +673,7 @@ struct Ctx {
 };
 
 template <int NS>
-__global__ void __launch_bounds__(kGT) td_grid_kernel(const GridParams P) {
+__global__ void __launch_bounds__(kGT, 1) td_grid_kernel(const GridParams P) {
     Ctx<NS> c(P);
     c.run();
 }
@@ -606,15 +701,15 @@ int td_grid_launch(const GridParams &P, int n_sm, cudaStream_t stream) {
     MCT_REQUIRE(P.ns >= 1 && P.ns <= kNsMax, MCT_UNSUPPORTED, "Ns > 4 is not supported on the device");
     const void *fn = P.ns == 1 ? (const void *)td_grid_kernel<1> : P.ns == 2 ? (const void *)td_grid_kernel<2>
                    : P.ns == 3 ? (const void *)td_grid_kernel<3> : (const void *)td_grid_kernel<4>;
-    // multi-component: five vectors of Nk doubles per block in shared memory (phase_lines)
-    const size_t smem = (P.type == GK_MC3D) ? (size_t)5 * P.Nk * sizeof(double) : 0;
+    // multi-component: five zero-padded vectors of Nk doubles per block in shared memory (phase_lines)
+    const size_t smem = (P.type == GK_MC3D) ? (size_t)20 * grid_chunks(P.Nk) * sizeof(double) : 0;
     MCT_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     MCT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kGT, smem));
     MCT_REQUIRE(per_sm >= 1, MCT_CUDA_ERROR, "cooperative kernel does not fit");
     GridParams Pc = P;
     void *args[] = {(void *)&Pc};
-    dim3 grid(n_sm * std::min(per_sm, 2)), block(kGT);
+    dim3 grid(n_sm), block(kGT);
     MCT_CUDA(cudaLaunchCooperativeKernel(fn, grid, block, args, smem, stream));
     count_launch();
     return MCT_OK;

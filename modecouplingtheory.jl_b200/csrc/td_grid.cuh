@@ -25,7 +25,7 @@ struct GridParams {
     double *C1, *C2, *C3, *Fold, *K0, *Fcur, *Kcur;   // [dof]
     double *G;                   // MC: F, G1, G2, G3 species-major [4][nb][Nk]
     double *Inc, *Tm;            // MC: increments and prefix sums [3*nb][Nk]
-    double *Lsum;                // line sums [3*Nk][3*nb]
+    double *Lsum;                // task sums [tasks][7][3*nb]  (grid_lsum_words)
     double *dFh;                 // bootstrap: dF history [2N+1][dof]
     unsigned long long *err;     // [2] rotating max-error words (bits of a non-negative double)
     double *F_out, *K_out;       // trajectory [nt][dof]  (mode 1/2: [dof])
@@ -34,12 +34,21 @@ struct GridParams {
     // them straight into every rank's exchange buffer (peer memory over NVLink, IPC-mapped); 4 rotating buffers of
     // self-validating words, each rank re-arms its own copy.  world == 1: single GPU, Lsum only.
     int rank, world;
-    double *xpeer[8];            // [world] exchange buffers [4][3*Nk*3*nb] of every rank (own included)
+    double *xpeer[8];            // [world] exchange buffers [4][grid_lsum_words] of every rank (own included)
     long long spin_limit_cycles;
     int *status;
     long long *kernel_evals;
     unsigned long long *prof;    // [12] cycles per phase seen by thread 0 (diagnostics, printed with MCT_GRID_PROF=1)
 };
+
+// Multi-component line sums are produced per tile task (td_grid.cu, phase_lines): 4-wavenumber chunks, one task per tile
+// diagonal J - I >= 0 (tasks [0, chunks)) and per tile antidiagonal that holds a line s <= Nk-2 (tasks chunks + S),
+// 7 lines x 3 vertices x Ns^2 words each.
+__host__ __device__ inline int grid_chunks(int Nk) { return (Nk + 3) / 4; }
+__host__ __device__ inline int grid_anti_tasks(int Nk) { return Nk >= 2 ? (Nk - 2) / 4 + 1 : 0; }
+__host__ __device__ inline size_t grid_lsum_words(int Nk, int ns) {
+    return (size_t)(grid_chunks(Nk) + grid_anti_tasks(Nk)) * 7 * 3 * ns * ns;
+}
 
 int td_grid_launch(const GridParams &P, int n_sm, cudaStream_t stream);
 
