@@ -482,7 +482,7 @@ static int grid_setup(mct_equation_t q, mct_kernel_t h, int mode, const std::vec
     g.dFh = p; p += dfh;
     g.F_out = p; g.K_out = p + traj; p += 2 * traj;
     g.err = (unsigned long long *)p; p += 2;
-    g.status = (int *)p; g.kernel_evals = (long long *)(p + 2); g.prof = (unsigned long long *)(p + 4);
+    g.status = (int *)p; g.kernel_evals = (long long *)(p + 2); g.prof = (unsigned long long *)(p + 4); g.xepoch_state = (unsigned *)(p + 32);
     q->d_F = g.F_out; q->d_K = g.K_out;
     return MCT_OK;
 }

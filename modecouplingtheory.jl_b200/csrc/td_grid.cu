@@ -127,6 +127,7 @@ struct Ctx {
         const int l = lane % GW;
         gbase = lane - l; gact = l < NB; ge = gact ? l : 0; ga = ge % NS; gb = ge / NS;
         tp = clock64();
+        xepoch = *p.xepoch_state;
     }
     __device__ __forceinline__ void mark(int slot) {
         if (gtid == 0) { const long long t = clock64(); P.prof[slot] += (unsigned long long)(t - tp); tp = t; }
@@ -199,7 +200,8 @@ struct Ctx {
     //      The (iq, ip) plane is cut into 4 x 4 tiles; a warp task is one tile diagonal (J - I = D >= 0: lines 4D-3 .. 4D+3)
     //      or tile antidiagonal (I + J = S: lines 4S .. 4S+6), its lanes stride over the tiles of the task.  Only d >= 0
     //      is walked: for a fixed species pair the entry at (ip, iq) equals the one at (iq, ip) (t1 <-> t4, t2 <-> t3 and
-    //      the sign of p^2 - q^2 swap together), so the line sums of d and -d are the same number.  A lane keeps
+    //      the sign of p^2 - q^2 swap together), so the line sums of d and -d are the same number, and an antidiagonal
+    //      is twice its half with iq < ip (plus the middle entry).  A lane keeps
     //      the 2 x 4 x 5 operands of a tile and 3 x 7 line accumulators in registers: 2.5 shared-memory words and 16
     //      FP64 operations per entry (10 and 28 when every entry is walked on its own), which is what bounds this phase.
     //      The 21 partial sums of a task are written per task; phase_scan adds the (at most two) tasks of a line.
@@ -262,7 +264,17 @@ struct Ctx {
 #pragma unroll
                 for (int i = 0; i < 8; i++) acc[m][i] = 0.0;
             int task;
-            if (kind == 1) { const int S = nc - lam - 1; task = nc + S; tile_walk<false>(gsm, nc, 0, S + 1, S, acc); }
+            if (kind == 1) {
+                // the mirror argument holds along an antidiagonal too: tiles I < J count twice, the middle tile (S even)
+                // holds both members of its pairs already
+                const int S = nc - lam - 1; task = nc + S;
+                tile_walk<false>(gsm, nc, 0, (S + 1) >> 1, S, acc);
+#pragma unroll
+                for (int m = 0; m < 3; m++)
+#pragma unroll
+                    for (int i = 0; i < 7; i++) acc[m][i] += acc[m][i];
+                if (!(S & 1)) tile_walk<false>(gsm, nc, (S >> 1) - lane, (S >> 1) + 1 - lane, S, acc);     // lane 0 alone
+            }
             else { task = lam; tile_walk<true>(gsm, nc, 0, nc - lam, lam, acc); }
             // 24 values (3 x 7 used) summed over the 32 lanes by halving: lanes exchange the half they do not keep
             double v12[12], v6[6], v4[4], v2[2];
@@ -676,6 +688,8 @@ template <int NS>
 __global__ void __launch_bounds__(kGT, 1) td_grid_kernel(const GridParams P) {
     Ctx<NS> c(P);
     c.run();
+    c.grid.sync();                                   // every thread has read the epoch word
+    if (c.gtid == 0) *P.xepoch_state = c.xepoch;
 }
 
 __global__ void ddim_table_kernel(int Nk, const double *V, const double *J, double prefactor, double *W) {

@@ -38,6 +38,8 @@ struct GridParams {
     long long spin_limit_cycles;
     int *status;
     long long *kernel_evals;
+    unsigned *xepoch_state;      // exchange epoch carried from one solve of a sharded equation to the next (the rotating
+                                 // buffers of all ranks stay in step without a host-side re-arm)
     unsigned long long *prof;    // [12] cycles per phase seen by thread 0 (diagnostics, printed with MCT_GRID_PROF=1)
 };
 
