@@ -207,17 +207,21 @@ struct Ctx {
     //      The 21 partial sums of a task are written per task; phase_scan adds the (at most two) tasks of a line.
     //      Tasks are dealt to warps longest first in snake order; rank r of a k-sharded solve takes every world-th task.
     template <bool DIAG>
-    __device__ __forceinline__ void tile_walk(const double *sm, int nc, int lo, int hi, int off, double (&acc)[3][8]) {
-        const double *sF = sm, *s1 = sm + 4 * nc, *s2 = sm + 8 * nc, *s3 = sm + 12 * nc, *sk = sm + 16 * nc;
-        auto ld4 = [](const double *p, double (&v)[4]) {
-            const double2 u = *reinterpret_cast<const double2 *>(p), w = *reinterpret_cast<const double2 *>(p + 2);
+    __device__ __forceinline__ void tile_walk(const double *sm, int gs, int lo, int hi, int off, double (&acc)[3][8]) {
+        const double *sF = sm, *s1 = sm + gs, *s2 = sm + 2 * gs, *s3 = sm + 3 * gs, *sk = sm + 4 * gs;
+        // the 4 operands of chunk I live in the 16-byte slots 2I and 2I+1, exchanged when bit 2 of I is set (swz): the 8
+        // lanes of a quarter warp then hit 8 different bank groups instead of 4 twice
+        auto ld4 = [](const double *p, int o0, int o1, double (&v)[4]) {
+            const double2 u = *reinterpret_cast<const double2 *>(p + o0), w = *reinterpret_cast<const double2 *>(p + o1);
             v[0] = u.x; v[1] = u.y; v[2] = w.x; v[3] = w.y;
         };
         for (int I = lo + lane; I < hi; I += 32) {
             const int J = DIAG ? I + off : off - I;
-            double xF[4], x1[4], x2[4], x3[4], xk[4], yF[4], y1[4], y2[4], y3[4], yk[4], xq[4], yp[4];
-            ld4(sF + 4 * I, xF); ld4(s1 + 4 * I, x1); ld4(s2 + 4 * I, x2); ld4(s3 + 4 * I, x3); ld4(sk + 4 * I, xk);
-            ld4(sF + 4 * J, yF); ld4(s1 + 4 * J, y1); ld4(s2 + 4 * J, y2); ld4(s3 + 4 * J, y3); ld4(sk + 4 * J, yk);
+            const int sx = (I >> 2) & 1, sy = (J >> 2) & 1;
+            const int x0 = 4 * I + 2 * sx, x1 = 4 * I + 2 - 2 * sx, y0 = 4 * J + 2 * sy, y1o = 4 * J + 2 - 2 * sy;
+            double xF[4], x1v[4], x2[4], x3[4], xk[4], yF[4], y1[4], y2[4], y3[4], yk[4], xq[4], yp[4];
+            ld4(sF, x0, x1, xF); ld4(s1, x0, x1, x1v); ld4(s2, x0, x1, x2); ld4(s3, x0, x1, x3); ld4(sk, x0, x1, xk);
+            ld4(sF, y0, y1o, yF); ld4(s1, y0, y1o, y1); ld4(s2, y0, y1o, y2); ld4(s3, y0, y1o, y3); ld4(sk, y0, y1o, yk);
 #pragma unroll
             for (int i = 0; i < 4; i++) { xq[i] = xk[i] * xk[i]; yp[i] = yk[i] * yk[i]; }
 #pragma unroll
@@ -226,7 +230,7 @@ struct Ctx {
                 for (int b = 0; b < 4; b++) {
                     const int idx = DIAG ? b - a + 3 : a + b;
                     const double pq2 = yp[b] - xq[a], P1 = yk[b] * xk[a], w = P1 * pq2, P2 = w * pq2;   // p = k[ip], q = k[iq]
-                    const double t1 = xF[a] * y1[b], t2 = y2[b] * x3[a], t3 = x2[a] * y3[b], t4 = x1[a] * yF[b];
+                    const double t1 = xF[a] * y1[b], t2 = y2[b] * x3[a], t3 = x2[a] * y3[b], t4 = x1v[a] * yF[b];
                     const double v = t1 + t4, u = t2 + t3;
                     acc[0][idx] = fma(v + u, P1, acc[0][idx]);       // :186-192 (V1: pq, V2: pq(p^2-q^2)^2, V3: 2pq(p^2-q^2))
                     acc[1][idx] = fma(v - u, P2, acc[1][idx]);
@@ -242,11 +246,13 @@ struct Ctx {
         xepoch++;
         const int e = blockIdx.x % NB;                       // species pair of this block
         const int chunk = blockIdx.x / NB, nchunk = (gridDim.x - e + NB - 1) / NB;    // blocks sharing this e
-        for (int i = threadIdx.x; i < 4 * nc; i += blockDim.x) {
+        const int gs = grid_smem_stride(Nk);
+        for (int i = threadIdx.x; i < gs; i += blockDim.x) {
             const bool in = i < Nk;
+            const int c = i >> 1, ph = ((c ^ ((c >> 3) & 1)) << 1) | (i & 1);      // swz: see tile_walk
 #pragma unroll
-            for (int j = 0; j < 4; j++) gsm[j * 4 * nc + i] = in ? P.G[(size_t)j * dof + (size_t)e * Nk + i] : 0.0;
-            gsm[16 * nc + i] = in ? P.kvec[i] : 0.0;
+            for (int j = 0; j < 4; j++) gsm[j * gs + ph] = in ? P.G[(size_t)j * dof + (size_t)e * Nk + i] : 0.0;
+            gsm[4 * gs + ph] = in ? P.kvec[i] : 0.0;
         }
         __syncthreads();
         const double pab = P.pref[e];
@@ -268,14 +274,14 @@ struct Ctx {
                 // the mirror argument holds along an antidiagonal too: tiles I < J count twice, the middle tile (S even)
                 // holds both members of its pairs already
                 const int S = nc - lam - 1; task = nc + S;
-                tile_walk<false>(gsm, nc, 0, (S + 1) >> 1, S, acc);
+                tile_walk<false>(gsm, gs, 0, (S + 1) >> 1, S, acc);
 #pragma unroll
                 for (int m = 0; m < 3; m++)
 #pragma unroll
                     for (int i = 0; i < 7; i++) acc[m][i] += acc[m][i];
-                if (!(S & 1)) tile_walk<false>(gsm, nc, (S >> 1) - lane, (S >> 1) + 1 - lane, S, acc);     // lane 0 alone
+                if (!(S & 1)) tile_walk<false>(gsm, gs, (S >> 1) - lane, (S >> 1) + 1 - lane, S, acc);     // lane 0 alone
             }
-            else { task = lam; tile_walk<true>(gsm, nc, 0, nc - lam, lam, acc); }
+            else { task = lam; tile_walk<true>(gsm, gs, 0, nc - lam, lam, acc); }
             // 24 values (3 x 7 used) summed over the 32 lanes by halving: lanes exchange the half they do not keep
             double v12[12], v6[6], v4[4], v2[2];
             {
@@ -716,7 +722,7 @@ int td_grid_launch(const GridParams &P, int n_sm, cudaStream_t stream) {
     const void *fn = P.ns == 1 ? (const void *)td_grid_kernel<1> : P.ns == 2 ? (const void *)td_grid_kernel<2>
                    : P.ns == 3 ? (const void *)td_grid_kernel<3> : (const void *)td_grid_kernel<4>;
     // multi-component: five zero-padded vectors of Nk doubles per block in shared memory (phase_lines)
-    const size_t smem = (P.type == GK_MC3D) ? (size_t)20 * grid_chunks(P.Nk) * sizeof(double) : 0;
+    const size_t smem = (P.type == GK_MC3D) ? (size_t)5 * grid_smem_stride(P.Nk) * sizeof(double) : 0;
     MCT_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     MCT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kGT, smem));

@@ -47,6 +47,7 @@ struct GridParams {
 // diagonal J - I >= 0 (tasks [0, chunks)) and per tile antidiagonal that holds a line s <= Nk-2 (tasks chunks + S),
 // 7 lines x 3 vertices x Ns^2 words each.
 __host__ __device__ inline int grid_chunks(int Nk) { return (Nk + 3) / 4; }
+__host__ __device__ inline int grid_smem_stride(int Nk) { return (4 * grid_chunks(Nk) + 15) / 16 * 16; }   // doubles per staged vector
 __host__ __device__ inline int grid_anti_tasks(int Nk) { return Nk >= 2 ? (Nk - 2) / 4 + 1 : 0; }
 __host__ __device__ inline size_t grid_lsum_words(int Nk, int ns) {
     return (size_t)(grid_chunks(Nk) + grid_anti_tasks(Nk)) * 7 * 3 * ns * ns;
