@@ -202,8 +202,8 @@ struct Ctx {
     //      is walked: for a fixed species pair the entry at (ip, iq) equals the one at (iq, ip) (t1 <-> t4, t2 <-> t3 and
     //      the sign of p^2 - q^2 swap together), so the line sums of d and -d are the same number, and an antidiagonal
     //      is twice its half with iq < ip (plus the middle entry).  A lane keeps
-    //      the 2 x 4 x 5 operands of a tile and 3 x 7 line accumulators in registers: 2.5 shared-memory words and 16
-    //      FP64 operations per entry (10 and 28 when every entry is walked on its own), which is what bounds this phase.
+    //      the 2 x 4 x 5 operands of a tile and 3 x 7 line accumulators in registers: 2.5 shared-memory words and 14
+    //      FP64 instructions per entry (10 and 28 when every entry is walked on its own), which is what bounds this phase.
     //      The 21 partial sums of a task are written per task; phase_scan adds the (at most two) tasks of a line.
     //      Tasks are dealt to warps longest first in snake order; rank r of a k-sharded solve takes every world-th task.
     template <bool DIAG>
@@ -230,11 +230,12 @@ struct Ctx {
                 for (int b = 0; b < 4; b++) {
                     const int idx = DIAG ? b - a + 3 : a + b;
                     const double pq2 = yp[b] - xq[a], P1 = yk[b] * xk[a], w = P1 * pq2, P2 = w * pq2;   // p = k[ip], q = k[iq]
-                    const double t1 = xF[a] * y1[b], t2 = y2[b] * x3[a], t3 = x2[a] * y3[b], t4 = x1v[a] * yF[b];
-                    const double v = t1 + t4, u = t2 + t3;
+                    // t1 = F_q G1_p, t2 = G2_p G3_q, t3 = G2_q G3_p, t4 = G1_q F_p; only t1 +- t4 and t2 + t3 are needed
+                    const double t4 = x1v[a] * yF[b], t3 = x2[a] * y3[b];
+                    const double v = fma(xF[a], y1[b], t4), dm = fma(xF[a], y1[b], -t4), u = fma(y2[b], x3[a], t3);
                     acc[0][idx] = fma(v + u, P1, acc[0][idx]);       // :186-192 (V1: pq, V2: pq(p^2-q^2)^2, V3: 2pq(p^2-q^2))
                     acc[1][idx] = fma(v - u, P2, acc[1][idx]);
-                    acc[2][idx] = fma(t1 - t4, w, acc[2][idx]);
+                    acc[2][idx] = fma(dm, w, acc[2][idx]);
                 }
         }
     }
