@@ -509,9 +509,11 @@ static int grid_run(mct_equation_t q, long long *evals, int *status, float *devi
     if (env_int("MCT_GRID_PROF", 0)) {
         unsigned long long pr[12];
         MCT_CUDA(cudaMemcpy(pr, q->gp.prof, sizeof(pr), cudaMemcpyDeviceToHost));
-        fprintf(stderr, "[mct] grid phases (cycles of thread 0, %lld evals, %.3f ms):", ev, ms);
-        for (int i = 0; i < 12; i++) fprintf(stderr, " %llu", pr[i]);
-        fprintf(stderr, "\n");
+        char line[512];
+        int n = snprintf(line, sizeof line, "[mct] rank %d grid phases (cycles of thread 0, %lld evals, %.3f ms):", q->gp.rank, ev, ms);
+        for (int i = 0; i < 12; i++) n += snprintf(line + n, sizeof line - n, " %llu", pr[i]);
+        snprintf(line + n, sizeof line - n, "\n");
+        fputs(line, stderr);
     }
     if (evals) *evals = ev;
     if (status) *status = st;
@@ -871,8 +873,10 @@ int mct_equation_shard_prepare(mct_equation_t q, int rank, int world, unsigned c
     MCT_REQUIRE(world >= 2 && world <= kMaxShardRanks && rank >= 0 && rank < world, MCT_BAD_ARGUMENT, "bad rank / world size (2..8)");
     MCT_CUDA(cudaSetDevice(q->kernel->device));
     const size_t xwords = grid_lsum_words(q->Nk, q->ns);
-    if (!q->d_xshard) MCT_CUDA(cudaMalloc(&q->d_xshard, 4 * xwords * sizeof(double)));
+    // 4 rotating buffers of task sums + 4 arrival counters (td_grid.cu, phase_lines / phase_scan)
+    if (!q->d_xshard) MCT_CUDA(cudaMalloc(&q->d_xshard, (4 * xwords + 8) * sizeof(double)));
     MCT_CUDA(cudaMemset(q->d_xshard, 0xFF, 4 * xwords * sizeof(double)));          // every slot armed with the sentinel
+    MCT_CUDA(cudaMemset(q->d_xshard + 4 * xwords, 0, 8 * sizeof(double)));
     cudaIpcMemHandle_t hd;
     MCT_CUDA(cudaIpcGetMemHandle(&hd, q->d_xshard));
     static_assert(sizeof(hd) == 64, "cudaIpcMemHandle_t is 64 bytes");

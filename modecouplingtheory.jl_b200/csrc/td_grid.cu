@@ -260,7 +260,8 @@ struct Ctx {
         const int wpb = blockDim.x >> 5, wi = chunk * wpb + (threadIdx.x >> 5), wstride = nchunk * wpb;
         for (int round = 0;; round++) {
             const int slot = round * wstride + ((round & 1) ? wstride - 1 - wi : wi);
-            const int t = slot * world + rank;               // position in the longest-first order
+            const int t = slot * world + (rank + slot) % world;   // position in the longest-first order; the rotation gives
+                                                                  // every rank both kinds of task when world is even
             if (round * wstride * world >= 2 * nc) break;
             if (t >= 2 * nc) continue;
             const int lam = t >> 1, kind = t & 1;            // task length nc - lam; kind 0: D = lam, 1: S = nc-lam-1
@@ -323,13 +324,6 @@ struct Ctx {
                 else for (int r = 0; r < world; r++) st_relaxed_sys(P.xpeer[r] + (size_t)(xepoch & 3u) * xwords + w, tot);
             }
         }
-        if (world > 1) {
-            // re-arm this rank's own copy of the buffer used two exchanges from now (every peer wrote it two exchanges ago
-            // and will write it again only after it has seen this rank's data of the next exchange)
-            unsigned long long *clr = (unsigned long long *)(P.xpeer[rank] + (size_t)((xepoch + 2u) & 3u) * xwords);
-            for (size_t i = gtid; i < xwords; i += gthreads) clr[i] = kSentinel;
-            __threadfence_system();
-        }
     }
 
     // ---- (3) bengtzelius3! (:2-43) as a prefix over the line sums.  One block per (m, e) sequence: its warps take
@@ -369,6 +363,17 @@ struct Ctx {
             double a = a0; if (two_a) a += a1;
             return ik > 0 ? (d + d) - a : d;
         };
+        if (world > 1 && ((int)blockIdx.x >= nseq || (int)gridDim.x <= nseq)) {
+            // The blocks without a sequence re-arm this rank's own copy of the buffer used two exchanges from now: every
+            // peer wrote it two exchanges ago and writes it again only after it has seen this rank's line sums of the
+            // next exchange, which leave after the grid barrier that ends this phase (the barrier's fence has put the
+            // sentinels in L2, where the peers' stores arrive, by then).
+            unsigned long long *clr = (unsigned long long *)(P.xpeer[P.rank] + (size_t)((xepoch + 2u) & 3u) * xwords);
+            const bool spare = (int)gridDim.x > nseq;
+            const size_t first = spare ? (size_t)(blockIdx.x - nseq) * blockDim.x + threadIdx.x : (size_t)gtid;
+            const size_t stride = spare ? (size_t)(gridDim.x - nseq) * blockDim.x : (size_t)gthreads;
+            for (size_t i = first; i < xwords; i += stride) clr[i] = kSentinel;
+        }
         const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
         const int seg = ((Nk + nw * 32 - 1) / (nw * 32)) * 32;
         const int b0 = min(Nk, w * seg), b1 = min(Nk, b0 + seg);
