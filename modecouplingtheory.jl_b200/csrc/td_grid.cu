@@ -93,12 +93,25 @@ __device__ __forceinline__ void blk_solve(const double *A, const double *B, doub
 
 constexpr unsigned long long kSentinel = 0xFFFFFFFFFFFFFFFFull;   // a NaN payload no arithmetic produces
 
-__device__ __forceinline__ void st_relaxed_sys(double *p, double v) {
-    asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
-}
 __device__ __forceinline__ unsigned long long ld_relaxed_sys_bits(const double *p) {
     unsigned long long v;
     asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// L2 load that the compiler can neither sink into the branch that uses the value nor merge: the prefix phase wants
+// all loads of a lane in flight before the first use (sunk loads cost one L2 round trip each, ~30 us per evaluation)
+__device__ __forceinline__ double ld_cg_now(const double *p) {
+    double v;
+    asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void red_add_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("red.relaxed.sys.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
 
@@ -321,8 +334,18 @@ struct Ctx {
                 tot *= (m == 2) ? 2.0 * pab : pab;
                 const size_t w = ((size_t)task * 7 + idx) * 3 * NB + m * NB + e;
                 if (world == 1) P.Lsum[w] = tot;
-                else for (int r = 0; r < world; r++) st_relaxed_sys(P.xpeer[r] + (size_t)(xepoch & 3u) * xwords + w, tot);
+                else P.xpeer[rank][(size_t)(xepoch & 3u) * xwords + w] = tot;       // this rank's own buffer; the peers pull
             }
+        }
+        if (world > 1) {
+            // announce: every block adds 1 to the arrival counter of this exchange on every rank once its sums are out
+            // (the sums are in this GPU's L2 -- where the peers' NVLink loads are served -- after the device-scope fence of
+            // every storing thread; the announcing thread adds the system-scope fence in front of its counter updates)
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) __threadfence_system();
+            if (threadIdx.x == 0)
+                for (int r = 0; r < world; r++) red_add_sys((unsigned long long *)(P.xpeer[r] + 4 * xwords) + (xepoch & 3u), 1ull);
         }
     }
 
@@ -334,45 +357,86 @@ struct Ctx {
         const int Nk = P.Nk, world = P.world, nseq = 3 * NB;
         const int nc = grid_chunks(Nk);
         const size_t xwords = grid_lsum_words(Nk, NS);
-        const double *lcur = (world > 1) ? P.xpeer[P.rank] + (size_t)(xepoch & 3u) * xwords : P.Lsum;
+        const double *lcur = P.Lsum;                           // sharded: filled by the landing pass below
         const long long t0 = clock64();
-        // line sums of other ranks arrive through NVLink: every word validates itself (sentinel until stored)
-        auto rd = [&](size_t w) -> double {
-            if (world == 1) return lcur[w];
-            unsigned long long v;
-            unsigned spins = 0;
-            while ((v = ld_relaxed_sys_bits(lcur + w)) == kSentinel) {
-                if ((++spins & 1023u) == 0 && clock64() - t0 > P.spin_limit_cycles) { failed = true; return 0.0; }
-            }
-            return __longlong_as_double((long long)v);
-        };
         // A line collects the entries of at most two tasks.  Increment of row ik (0-based): diagonal ik + diagonal -ik
         // (the same number, see phase_lines) - antidiagonal ik-1; ik = 0: the main diagonal alone.  Word addresses are
-        // clamped and the values selected afterwards so that the loads of a lane are independent of each other.
-        auto increment = [&](int ik, int c) -> double {
-            const int D0 = ik >> 2, r = ik & 3;
-            const bool two_d = r > 0 && D0 + 1 <= nc - 1;
-            const size_t wd0 = ((size_t)D0 * 7 + r + 3) * nseq + c, wd1 = ((size_t)(two_d ? D0 + 1 : D0) * 7 + (two_d ? r - 1 : r + 3)) * nseq + c;
+        // clamped so that the 4 loads of a row are unconditional; the values are selected afterwards.
+        struct Row { size_t w[4]; bool two_d, two_a, pos; };
+        auto row_of = [&](int ik, int c) {
+            Row r;
+            const int D0 = ik >> 2, rr = ik & 3;
+            r.two_d = rr > 0 && D0 + 1 <= nc - 1;
+            r.w[0] = ((size_t)D0 * 7 + rr + 3) * nseq + c;
+            r.w[1] = ((size_t)(r.two_d ? D0 + 1 : D0) * 7 + (r.two_d ? rr - 1 : rr + 3)) * nseq + c;
             const int s_ = max(ik - 1, 0), S0 = s_ >> 2, q = s_ & 3;
-            const bool two_a = q <= 2 && S0 >= 1;
-            const size_t wa0 = ((size_t)(nc + S0) * 7 + q) * nseq + c, wa1 = ((size_t)(nc + (two_a ? S0 - 1 : S0)) * 7 + (two_a ? q + 4 : q)) * nseq + c;
-            double d0, d1, a0, a1;
-            if (world == 1) { d0 = lcur[wd0]; d1 = lcur[wd1]; a0 = lcur[wa0]; a1 = lcur[wa1]; }
-            else { d0 = rd(wd0); d1 = two_d ? rd(wd1) : 0.0; a0 = ik > 0 ? rd(wa0) : 0.0; a1 = (ik > 0 && two_a) ? rd(wa1) : 0.0; }
-            double d = d0; if (two_d) d += d1;
-            double a = a0; if (two_a) a += a1;
-            return ik > 0 ? (d + d) - a : d;
+            r.two_a = q <= 2 && S0 >= 1;
+            r.w[2] = ((size_t)(nc + S0) * 7 + q) * nseq + c;
+            r.w[3] = ((size_t)(nc + (r.two_a ? S0 - 1 : S0)) * 7 + (r.two_a ? q + 4 : q)) * nseq + c;
+            r.pos = ik > 0;
+            if (!r.pos) { r.w[2] = r.w[0]; r.w[3] = r.w[0]; }          // row 0 has no antidiagonal: any valid word
+            return r;
         };
-        if (world > 1 && ((int)blockIdx.x >= nseq || (int)gridDim.x <= nseq)) {
-            // The blocks without a sequence re-arm this rank's own copy of the buffer used two exchanges from now: every
-            // peer wrote it two exchanges ago and writes it again only after it has seen this rank's line sums of the
-            // next exchange, which leave after the grid barrier that ends this phase (the barrier's fence has put the
-            // sentinels in L2, where the peers' stores arrive, by then).
+        auto combine = [&](const Row &r, const double (&v)[4]) -> double {
+            double d = v[0]; if (r.two_d) d += v[1];
+            double a = v[2]; if (r.two_a) a += v[3];
+            return r.pos ? (d + d) - a : d;
+        };
+        auto increment = [&](int ik, int c) -> double {
+            const Row r = row_of(ik, c);
+            double v[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) v[i] = ld_cg_now(lcur + r.w[i]);
+            return combine(r, v);
+        };
+        if (world > 1) {
+            // Landing pass of a k-sharded solve.  One thread per block waits for the arrival counter of this exchange (all
+            // blocks of all ranks have announced); then the grid PULLS every task's sums from the buffer of the rank that
+            // computed it (NVLink loads from peer memory, unit stride within a task) into the local Lsum, and re-arms this
+            // rank's own buffer of two exchanges ahead.  Every word still validates itself (sentinel until stored).
+            if (threadIdx.x == 0) {
+                const unsigned long long *cnt = (const unsigned long long *)(P.xpeer[P.rank] + 4 * xwords) + (xepoch & 3u);
+                const unsigned long long want = (unsigned long long)world * gridDim.x;
+                unsigned spins = 0;
+                while (ld_acquire_sys(cnt) < want)
+                    if ((++spins & 255u) == 0 && clock64() - t0 > P.spin_limit_cycles) { failed = true; break; }
+            }
+            __syncthreads();
+            const size_t slot_off = (size_t)(xepoch & 3u) * xwords;
             unsigned long long *clr = (unsigned long long *)(P.xpeer[P.rank] + (size_t)((xepoch + 2u) & 3u) * xwords);
-            const bool spare = (int)gridDim.x > nseq;
-            const size_t first = spare ? (size_t)(blockIdx.x - nseq) * blockDim.x + threadIdx.x : (size_t)gtid;
-            const size_t stride = spare ? (size_t)(gridDim.x - nseq) * blockDim.x : (size_t)gthreads;
-            for (size_t i = first; i < xwords; i += stride) clr[i] = kSentinel;
+            const int rec = 21 * NB;                               // words per task
+            auto source = [&](size_t i) -> const double * {
+                const int task = (int)(i / rec);
+                const int t = task < nc ? 2 * task : 2 * (2 * nc - task - 1) + 1;       // position in the dealing order (phase_lines)
+                const int slot = t / world, owner = ((t - slot * world) - slot % world + world) % world;
+                return P.xpeer[owner] + slot_off + i;
+            };
+            constexpr int kU = 12;                                 // remote loads in flight per thread (one NVLink round trip each)
+            for (size_t i0 = gtid; i0 < xwords; i0 += (size_t)gthreads * kU) {
+                double v[kU];
+#pragma unroll
+                for (int u = 0; u < kU; u++) {
+                    const size_t i = i0 + (size_t)u * gthreads;
+                    v[u] = ld_cg_now(source(i < xwords ? i : i0));
+                }
+#pragma unroll
+                for (int u = 0; u < kU; u++) {
+                    const size_t i = i0 + (size_t)u * gthreads;
+                    if (i >= xwords) continue;
+                    unsigned long long bits = (unsigned long long)__double_as_longlong(v[u]);
+                    unsigned spins = 0;
+                    while (bits == kSentinel) {
+                        bits = ld_relaxed_sys_bits(source(i));
+                        if ((++spins & 1023u) == 0 && clock64() - t0 > P.spin_limit_cycles) { failed = true; break; }
+                    }
+                    P.Lsum[i] = __longlong_as_double((long long)bits);
+                    clr[i] = kSentinel;
+                }
+            }
+            if (gtid == 0) ((unsigned long long *)(P.xpeer[P.rank] + 4 * xwords))[(xepoch + 2u) & 3u] = 0ull;
+            if (failed) *P.status = MCT_CUDA_ERROR;
+            grid.sync();
+            failed = false;
         }
         const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
         const int seg = ((Nk + nw * 32 - 1) / (nw * 32)) * 32;
@@ -382,9 +446,15 @@ struct Ctx {
             double *Tm = P.Tm + (size_t)c * Nk;
             double carry = 0.0;
             if (seg <= 32 * kFast) {
-                double v[kFast];
+                double v[kFast], raw[kFast][4];
 #pragma unroll
-                for (int j = 0; j < kFast; j++) { const int ik = b0 + 32 * j + lane; v[j] = (ik < b1) ? increment(ik, c) : 0.0; }
+                for (int j = 0; j < kFast; j++) {                  // rows past the segment load row Nk-1 and are dropped
+                    const Row r = row_of(min(b0 + 32 * j + lane, Nk - 1), c);
+#pragma unroll
+                    for (int i = 0; i < 4; i++) raw[j][i] = ld_cg_now(lcur + r.w[i]);
+                }
+#pragma unroll
+                for (int j = 0; j < kFast; j++) { const int ik = b0 + 32 * j + lane; v[j] = (ik < b1) ? combine(row_of(min(ik, Nk - 1), c), raw[j]) : 0.0; }
 #pragma unroll
                 for (int j = 0; j < kFast; j++) {
 #pragma unroll
