@@ -139,6 +139,16 @@ MCT_API int mct_equation_solve_batch(int n, mct_equation_t *eqs, int *status, lo
 MCT_API int mct_equation_shard_prepare(mct_equation_t eq, int rank, int world, unsigned char *handle_out /* 64 bytes */);
 MCT_API int mct_equation_shard_connect(mct_equation_t eq, const unsigned char *handles /* [world][64] */);
 
+/* MSDModeCouplingKernel(rho, kBT, m, k_array, S, sol, taggedsol) (src/Kernels/ModeCouplingKernels.jl:552-570) and
+ * solve(MemoryEquation(alpha, beta, gamma, delta, MSD0, dMSD0, kernel), TimeDoublingSolver) for it
+ * (src/TimeDoublingSolver.jl:512-532, scalar/immutable branch :213-235).  `collective` and `tagged` are the two solved
+ * device-resident equations (same grid, same solver options -- the reference's tDict lookup); the kernel table
+ * K(t_i) (:572-586) is reduced on the device from their trajectories, nothing but nt-sized vectors crosses PCIe.
+ * Sk: Nk doubles (host).  t_out, msd_out, K_out: nt doubles. */
+MCT_API int mct_msd3d_solve(mct_equation_t collective, mct_equation_t tagged, double rho, double kBT, double m, const double *Sk,
+                    double alpha, double beta, double gamma, double delta, double MSD0, double dMSD0,
+                    double *t_out, double *msd_out, double *K_out, long *kernel_evals);
+
 /* solve_steady_state(gamma, F0, kernel; tolerance, max_iterations)  src/SteadyStateMemoryEquation.jl:59-100.
  * gamma: dof doubles (Diagonal / blocks).  F_out, K_out: dof doubles. */
 MCT_API int mct_steady_state(mct_kernel_t kernel, const double *gamma, const double *F0, double tolerance, long max_iterations,

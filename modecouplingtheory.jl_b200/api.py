@@ -53,7 +53,7 @@ EXPORTS = [
     "mct_sc3d_tagged_create", "mct_sc3d_tagged_create_from_sk", "mct_sc3d_tagged_create_from_equation", "mct_mc3d_create",
     "mct_ddim_create", "mct_kernel_eval", "mct_kernel_eval_many", "mct_kernel_destroy", "mct_td_output_len", "mct_td_solve",
     "mct_equation_create", "mct_equation_solve", "mct_equation_download", "mct_equation_destroy", "mct_equation_solve_batch", "mct_equation_shard_prepare", "mct_equation_shard_connect",
-    "mct_steady_state",
+    "mct_steady_state", "mct_msd3d_solve",
 ]
 
 
@@ -205,6 +205,50 @@ def TaggedModeCouplingKernel(rho, kBT, m, k_array, Sk, sol, dims=3, device=0, ta
         _check(L.mct_sc3d_tagged_create(C.byref(h), device, len(k), _p(k), _p(V[0]), _p(V[1]), _p(V[2]),
                                         C.c_long(Fc.shape[0]), _p(Fc)))
     return MemoryKernel(h, len(k), 1, device)
+
+
+class MSDKernel:
+    """MSDModeCouplingKernel(ρ, kBT, m, k_array, Sₖ, sol, taggedsol; dims=3) -- src/Kernels/ModeCouplingKernels.jl:552-570.
+    Holds the two device-resident solutions; `solve` of a scalar MemoryEquation with this kernel runs
+    `mct_msd3d_solve` (kernel table reduced on the device, scalar time doubling in one device thread)."""
+    Ns = 1
+    dof = 1
+
+    def __init__(self, rho, kBT, m, k_array, Sk, sol, taggedsol):
+        if getattr(sol, "_equation", None) is None or getattr(taggedsol, "_equation", None) is None:
+            raise MCTDeviceError("MSDModeCouplingKernel needs the device-resident solutions (solve(..., keep_device=True))")
+        self.rho, self.kBT, self.m = float(rho), float(kBT), float(m)
+        self.k = _arr(k_array)
+        self.Sk = _arr(Sk)
+        self.sol, self.taggedsol = sol, taggedsol
+
+
+def MSDModeCouplingKernel(rho, kBT, m, k_array, Sk, sol, taggedsol, dims=3):
+    if dims != 3:
+        raise NotImplementedError("dDimMSDModeCouplingKernel is not implemented on the device yet")
+    return MSDKernel(rho, kBT, m, k_array, Sk, sol, taggedsol)
+
+
+def _solve_msd(equation, solver):
+    L = load_library()
+    kern = equation.kernel
+    for name in ("alpha", "beta", "gamma"):
+        if not isinstance(equation.coeffs[name], float):
+            raise MCTDeviceError("the MSD equation is scalar: coefficients must be numbers")
+    q = kern.sol._equation
+    nt = kern.sol.F.shape[0]
+    if solver.output_len() != nt:
+        raise MCTDeviceError("the MSD solve must use the solver options of the collective solve (same time grid)")
+    t = np.empty(nt); F = np.empty(nt); K = np.empty(nt)
+    evals = C.c_long(0)
+    delta = 0.0 if equation.delta is None else float(equation.delta[0])
+    rc = L.mct_msd3d_solve(q._q, kern.taggedsol._equation._q, C.c_double(kern.rho), C.c_double(kern.kBT), C.c_double(kern.m),
+                           _p(kern.Sk), C.c_double(equation.coeffs["alpha"]), C.c_double(equation.coeffs["beta"]),
+                           C.c_double(equation.coeffs["gamma"]), C.c_double(delta), C.c_double(float(equation.F0[0])),
+                           C.c_double(float(equation.dF0[0])), _p(t), _p(F), _p(K), C.byref(evals))
+    solver.kernel_evals = evals.value
+    _check(rc)
+    return MemoryEquationSolution(t, F, K, solver)
 
 
 def _to_blocks(X):
@@ -426,6 +470,8 @@ def solve(equation, solver=None, keep_device=True):
     """solve(equation, solver) -- src/Solvers.jl:42-46, src/TimeDoublingSolver.jl:512-532.
     Writes solver.kernel_evals like the reference (:416, :520)."""
     solver = solver or TimeDoublingSolver()
+    if isinstance(equation.kernel, MSDKernel):
+        return _solve_msd(equation, solver)
     L = load_library()
     dev_eq = _create_equation(equation, solver)
     evals = C.c_long(0)

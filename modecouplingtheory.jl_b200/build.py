@@ -10,7 +10,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(LIBDIR, "obj")
 LIB = os.path.join(LIBDIR, "libmct_sm100a.so")
-SOURCES = ["abi.cu", "layout.cu", "eval.cu", "td_sc.cu", "td_sc_k1.cu", "td_sc_k2.cu", "td_sc_k4.cu", "td_sc_k8.cu", "td_grid.cu"]
+SOURCES = ["abi.cu", "layout.cu", "eval.cu", "td_sc.cu", "td_sc_k1.cu", "td_sc_k2.cu", "td_sc_k4.cu", "td_sc_k8.cu", "td_grid.cu", "msd.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-fmad=false",            # reference-order arithmetic: FMAs only where the code asks for them with fma()

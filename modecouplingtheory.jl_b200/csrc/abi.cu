@@ -10,6 +10,7 @@
 
 #include "common.cuh"
 #include "eval.cuh"
+#include "msd.cuh"
 #include "layout.cuh"
 #include "td_grid.cuh"
 #include "td_sc.cuh"
@@ -898,6 +899,60 @@ int mct_equation_shard_connect(mct_equation_t q, const unsigned char *handles) {
         q->gp.xpeer[r] = (double *)p;
     }
     return MCT_OK;
+}
+
+int mct_msd3d_solve(mct_equation_t collective, mct_equation_t tagged, double rho, double kBT, double m, const double *Sk,
+                    double alpha, double beta, double gamma, double delta, double MSD0, double dMSD0,
+                    double *t_out, double *msd_out, double *K_out, long *kernel_evals) {
+    MCT_REQUIRE(collective && tagged && Sk && t_out && msd_out && K_out, MCT_BAD_ARGUMENT, "NULL argument to mct_msd3d_solve");
+    MCT_REQUIRE(collective->solved && tagged->solved, MCT_BAD_ARGUMENT, "both equations must have been solved on the device");
+    MCT_REQUIRE(collective->ns == 1 && tagged->ns == 1 && !collective->d_gws && !tagged->d_gws, MCT_UNSUPPORTED,
+                "the MSD kernel is implemented for single-component solutions");
+    MCT_REQUIRE(collective->Nk == tagged->Nk && collective->nt == tagged->nt && collective->opts.N == tagged->opts.N &&
+                    collective->opts.dt == tagged->opts.dt,
+                MCT_BAD_ARGUMENT, "the two solutions must share the wavenumber grid and the time grid (tDict lookup)");
+    MCT_REQUIRE(collective->kernel->device == tagged->kernel->device, MCT_BAD_ARGUMENT, "the two solutions live on different devices");
+    MCT_REQUIRE(alpha != 0.0 || beta != 0.0, MCT_BAD_ARGUMENT, "alpha and beta are both zero");
+    mct_kernel_t h = collective->kernel;
+    const int Nk = collective->Nk;
+    const long nt = collective->nt;
+    MCT_CUDA(cudaSetDevice(h->device));
+    std::vector<double> kh(Nk), ck(Nk);
+    MCT_CUDA(cudaMemcpy(kh.data(), h->d_k, Nk * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < Nk; i++) ck[i] = (Sk[i] - 1.0) / (rho * Sk[i]);             // ModeCouplingKernels.jl:566
+    const double dk = kh[1] - kh[0];
+    const double pi = 3.14159265358979323846;
+    double *d = nullptr;                                  // Ck [Nk], Ktab [nt], t/F/K out [3 nt], status, evals
+    MCT_CUDA(cudaMalloc(&d, ((size_t)Nk + 4 * nt + 4) * sizeof(double)));
+    cudaError_t e = cudaMemcpy(d, ck.data(), Nk * sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemset(d + Nk + 4 * nt, 0, 4 * sizeof(double));
+    if (e != cudaSuccess) { cudaFree(d); return cuda_fail(e, "mct_msd3d_solve setup", __FILE__, __LINE__); }
+    MsdParams P{};
+    P.Nk = Nk; P.N = collective->opts.N; P.nblocks = collective->nblocks; P.nt = nt;
+    P.dt0 = collective->opts.dt; P.tol = collective->opts.tolerance; P.max_iter = collective->opts.max_iterations;
+    P.alpha = alpha; P.beta = beta; P.gamma = gamma; P.delta = delta; P.F0 = MSD0; P.dF0 = dMSD0;
+    P.scale = dk * rho * kBT / (6.0 * (pi * pi) * m);                               // :583
+    P.kvec = h->d_k; P.Ck = d; P.Fc = collective->d_F; P.Fs = tagged->d_F;
+    P.Ktab = d + Nk; P.t_out = d + Nk + nt; P.F_out = d + Nk + 2 * nt; P.K_out = d + Nk + 3 * nt;
+    P.status = (int *)(d + Nk + 4 * nt); P.kernel_evals = (long long *)(d + Nk + 4 * nt + 2);
+    int rc = msd3d_launch(P, h->stream);
+    if (rc == MCT_OK) {
+        e = cudaStreamSynchronize(h->stream);
+        if (e == cudaSuccess) e = cudaMemcpy(t_out, P.t_out, nt * sizeof(double), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(msd_out, P.F_out, nt * sizeof(double), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(K_out, P.K_out, nt * sizeof(double), cudaMemcpyDeviceToHost);
+        int st = 0; long long ev = 0;
+        if (e == cudaSuccess) e = cudaMemcpy(&st, P.status, sizeof(int), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(&ev, P.kernel_evals, sizeof(long long), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = cuda_fail(e, "mct_msd3d_solve", __FILE__, __LINE__);
+        else {
+            if (kernel_evals) *kernel_evals = (long)ev;
+            rc = st;
+            if (rc == MCT_NOT_CONVERGED) set_error("Iteration did not converge.");
+        }
+    }
+    cudaFree(d);
+    return rc;
 }
 
 int mct_steady_state(mct_kernel_t h, const double *gamma, const double *F0, double tolerance, long max_iterations,

@@ -1,0 +1,150 @@
+// msd.cu -- MSDModeCouplingKernel3D and the scalar memory equation it feeds.
+//
+// evaluate_kernel(kernel::MSDModeCouplingKernel3D, MSD, t) (src/Kernels/ModeCouplingKernels.jl:572-586) does not depend
+// on the unknown: K(t_i) = dk rho kBT / (6 pi^2 m) * sum_q q^4 c_q^2 F(q,t_i) Fs(q,t_i), with F and Fs the trajectories
+// of the collective and the tagged solve looked up at the same time (tDict).  Both trajectories are resident on the
+// device after their solves, so the table is one pass over 2 nt Nk doubles (HBM-bound) and nothing crosses PCIe.
+// The equation itself is scalar: `solve` takes the allocating branch for an immutable F0 (compute_C3_immutable,
+// src/TimeDoublingSolver.jl:213-235; F_old restored from the cache every step, :400).  One thread integrates it.
+#include "msd.cuh"
+
+namespace mct {
+
+namespace {
+
+// one block per output time; left-to-right partial sums per thread, fixed-order tree afterwards
+__global__ void msd_table_kernel(const MsdParams P) {
+    __shared__ double red[kWarps];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (long it = blockIdx.x; it < P.nt; it += gridDim.x) {
+        const double *F = P.Fc + (size_t)it * P.Nk, *Fs = P.Fs + (size_t)it * P.Nk;
+        double s = 0.0;
+        for (int iq = threadIdx.x; iq < P.Nk; iq += blockDim.x) {
+            const double k = P.kvec[iq], c = P.Ck[iq];
+            s += k * k * k * k * (c * c) * F[iq] * Fs[iq];           // :581
+        }
+        s = warp_sum(s);
+        if (lane == 0) red[w] = s;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int i = 0; i < kWarps; i++) t += red[i];
+            P.Ktab[it] = t * P.scale;                                // :583
+        }
+        __syncthreads();
+    }
+}
+
+// scalar time doubling with a tabulated kernel; rings in shared memory (slot s at index s-1)
+__global__ void msd_scalar_td_kernel(const MsdParams P) {
+    extern __shared__ double sm[];
+    if (threadIdx.x != 0) return;
+    const int N = P.N, n4 = 4 * N, n2 = 2 * N;
+    double *Ft = sm, *Kt = sm + n4, *FI = sm + 2 * n4, *KI = sm + 3 * n4;
+    double *Karr = sm + 4 * n4, *dFarr = Karr + (n2 + 1), *Farr = dFarr + (n2 + 1);
+#define FT(s) Ft[(s) - 1]
+#define KT(s) Kt[(s) - 1]
+#define FINT(s) FI[(s) - 1]
+#define KINT(s) KI[(s) - 1]
+    const double a = P.alpha, b = P.beta, g = P.gamma, dlt0 = P.delta;
+    const double K0 = P.Ktab[0];                                     // src/MemoryEquation.jl:45
+    const double Fold0 = K0 * P.F0;                                  // :64
+    for (int s = 1; s <= n4; s++) { FT(s) = Fold0; FINT(s) = Fold0; KT(s) = K0 + K0; KINT(s) = K0 + K0; }   // :82-85
+    // Euler bootstrap  src/EulerSolver.jl:26-64, 92-112
+    const double de = P.dt0 / (4.0 * N);
+    Karr[0] = K0; dFarr[0] = P.dF0; Farr[0] = P.F0;
+    for (int it = 1; it <= n2; it++) {
+        double integ;
+        if (it == 1) integ = Karr[0] * dFarr[0] * de;                // :34-36
+        else {
+            double r = Karr[0] * dFarr[it - 1] / 2.0;
+            r += Karr[it - 1] * dFarr[0] / 2.0;
+            for (int i = 2; i <= it - 1; i++) r += Karr[i - 1] * dFarr[it - i];
+            integ = r * de;
+        }
+        const double Fo = Farr[it - 1], dFo = dFarr[it - 1];
+        if (a != 0.0) {                                              // :55-58
+            const double ddF = (b * dFo + g * Fo + dlt0 + integ) / (-a);
+            dFarr[it] = dFo + de * ddF;
+            Farr[it] = Fo + de * dFarr[it];
+        } else {                                                     // :60-61
+            const double dF = (g * Fo + dlt0 + integ) / (-b);
+            dFarr[it] = dF;
+            Farr[it] = Fo + de * dF;
+        }
+        Karr[it] = P.Ktab[it];
+    }
+    for (int it = 1; it <= n2; it++) { FT(it) = Farr[it]; KT(it) = Karr[it]; }       // :96-109, :155-166
+    FINT(1) = (FT(1) + P.F0) / 2.0;                                  // initialize_integrals! :174-199
+    KINT(1) = (3.0 * KT(1) - KT(2)) / 2.0;
+    for (int it = 2; it <= n2; it++) { FINT(it) = (FT(it) + FT(it - 1)) / 2.0; KINT(it) = (KT(it) + KT(it - 1)) / 2.0; }
+    long nout = 0;
+    P.t_out[0] = 0.0; P.F_out[0] = P.F0; P.K_out[0] = K0; nout = 1;
+    for (int it = 1; it <= n2; it++, nout++) { P.t_out[nout] = de * it; P.F_out[nout] = FT(it); P.K_out[nout] = KT(it); }
+    long long evals = 0;
+    int status = MCT_OK;
+    double Dt = P.dt0;
+    for (int blk = 0; blk < P.nblocks && status == MCT_OK; blk++, Dt *= 2.0) {
+        const double dl = Dt / (4.0 * N);
+        for (int it = n2 + 1; it <= n4 && status == MCT_OK; it++) {
+            const int i2 = it / 2;
+            double Fold = Fold0;                                     // immutable branch: F_old from the cache  :400
+            const double c1 = ((2.0 / (dl * dl) * a + 3.0 / (2.0 * dl) * b) + KINT(1)) + g;     // :310
+            const double c2 = FINT(1) - P.F0;                        // :311
+            double c3 = a * (5.0 * FT(it - 1) - 4.0 * FT(it - 2) + FT(it - 3)) / (dl * dl);    // compute_C3_immutable :213-235
+            c3 += b * (2.0 / dl * FT(it - 1) - FT(it - 2) / (2.0 * dl));
+            c3 -= dlt0;
+            c3 += -KT(it - i2) * FT(i2) + KT(it - 1) * FINT(1) + KINT(1) * FT(it - 1);
+            for (int j = 2; j <= i2; j++) c3 += (KT(it - j) - KT(it - j + 1)) * FINT(j);
+            for (int j = 2; j <= it - i2; j++) c3 += KINT(j) * (FT(it - j) - FT(it - j + 1));
+            FT(it) = (-KT(it) * c2 + c3) / c1;                       // update_F! with the stale K_temp[it]  :330-331
+            double err = INFINITY;
+            long long iter = 0;
+            while (err > P.tol) {                                    // :404
+                iter++;
+                if (iter > P.max_iter) { status = MCT_NOT_CONVERGED; break; }
+                KT(it) = P.Ktab[nout + (it - n2 - 1)];               // update_K!: the table at this step's time  :364-365
+                FT(it) = (-KT(it) * c2 + c3) / c1;
+                err = fabs(FT(it) - Fold);                           // :410
+                Fold = FT(it);
+                evals++;                                             // :416
+            }
+            if (status != MCT_OK) break;
+            FINT(it) = (FT(it) + FT(it - 1)) / 2.0;                  // update_integrals! :377-384
+            KINT(it) = (KT(it) + KT(it - 1)) / 2.0;
+        }
+        if (status != MCT_OK) break;
+        for (int it = n2 + 1; it <= n4; it++, nout++) { P.t_out[nout] = dl * it; P.F_out[nout] = FT(it); P.K_out[nout] = KT(it); }   // :429-438
+        for (int j = 1; j <= n2; j++) {                              // new_time_mapping! :448-489
+            FINT(j) = (FINT(2 * j) + FINT(2 * j - 1)) / 2.0;
+            KINT(j) = (KINT(2 * j) + KINT(2 * j - 1)) / 2.0;
+            FT(j) = FT(2 * j);
+            KT(j) = KT(2 * j);
+        }
+        for (int j = n2 + 1; j <= n4; j++) { FINT(j) = 0.0; KINT(j) = 0.0; FT(j) = 0.0; KT(j) = 0.0; }
+    }
+    *P.status = status;
+    *P.kernel_evals = evals;
+#undef FT
+#undef KT
+#undef FINT
+#undef KINT
+}
+
+}  // namespace
+
+int msd3d_launch(const MsdParams &P, cudaStream_t stream) {
+    const int blocks = (int)std::min<long>(P.nt, 148 * 8);
+    msd_table_kernel<<<blocks, kThreads, 0, stream>>>(P);
+    count_launch();
+    MCT_CUDA(cudaGetLastError());
+    const size_t smem = ((size_t)16 * P.N + 3 * (2 * P.N + 1)) * sizeof(double);
+    MCT_REQUIRE(smem <= 200 * 1024, MCT_UNSUPPORTED, "N too large for the scalar device solver");
+    MCT_CUDA(cudaFuncSetAttribute((const void *)msd_scalar_td_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    msd_scalar_td_kernel<<<1, 32, smem, stream>>>(P);
+    count_launch();
+    MCT_CUDA(cudaGetLastError());
+    return MCT_OK;
+}
+
+}  // namespace mct

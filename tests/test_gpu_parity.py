@@ -187,6 +187,16 @@ def test_newtonian_golden_test_tagged_59_and_tagged_chain():
     Kmsd = O.msd3d_table(p["rho"], 1.0, 1.0, p["k"], p["Sk"], sol.F, sols.F)
     msd = O.td_solve(O.tabulated(Kmsd), 1.0, 0.0, 0.0, -6.0, [0.0], [0.0], scalar_mode=True, **kw)
     assert msd["F"].sum() == pytest.approx(51.75329405084479, rel=1.5e-8)
+    # the same on the device: kernel table reduced from the two resident trajectories, the scalar equation
+    # integrated by one device thread in the reference's immutable-branch order
+    mk = pkg.MSDModeCouplingKernel(p["rho"], 1.0, 1.0, p["k"], p["Sk"], sol, sols)
+    msolver = pkg.TimeDoublingSolver(**kw)
+    msol = pkg.solve(pkg.MemoryEquation(1.0, 0.0, 0.0, -6.0, 0.0, 0.0, mk), msolver)
+    assert msol.F.sum() == pytest.approx(51.75329405084479, rel=1.5e-8)            # test/test_tagged.jl:71
+    assert np.allclose(msol.K, Kmsd, rtol=1e-12, atol=0)
+    assert np.allclose(msol.t, msd["t"], rtol=0, atol=0)
+    assert np.max(np.abs(msol.F - np.ravel(msd["F"]))) <= 1e-10 * max(1.0, np.max(np.abs(msd["F"])))
+    assert msolver.kernel_evals == msd["kernel_evals"]
 
 
 def test_relaxation_time_near_critical_point_docs_Scope_230():
