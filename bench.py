@@ -205,12 +205,15 @@ def run_sweep_workload(args, pkg, torch, dist, rank, world, dev):
     etas = np.linspace(0.50, 0.53, args.points)
     mine = sw.partition(sw.expected_cost(etas), world, rank)
     kpeak = int(np.argmin(np.abs(pkg.structure_factors.wavenumber_grid(args.sweep_nk) - 7.0)))
-    obs = lambda sol: np.array([sol.F[-1, kpeak] / sol.F[0, kpeak]])
+    nt = pkg.TimeDoublingSolver().output_len()
+    # only F(k_peak, t=0) and F(k_peak, t_end) of every solution cross PCIe (mct_equation_download_slice)
+    obs = lambda sol: np.array([sol.F[-1, 0] / sol.F[0, 0]])
+    slice_ = dict(times=[0, nt - 1], dofs=[kpeak], K=False)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
-    vals, evals, ms = sw.run_sweep(pkg, etas[mine], args.sweep_nk, dev, batch=64, observable=obs)
+    vals, evals, ms = sw.run_sweep(pkg, etas[mine], args.sweep_nk, dev, batch=64, observable=obs, download=slice_)
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     stats = torch.tensor([wall, ms], dtype=torch.float64, device=f"cuda:{dev}")

@@ -80,6 +80,7 @@ MCT_API int mct_ddim_create(mct_kernel_t *out, int device, int Nk, const double 
 MCT_API int mct_kernel_eval(mct_kernel_t kernel, const double *F, long t_index, double *out);
 /* n independent evaluations K_b = kernel(F_b), F and out are [n][dof] (parity tests, roofline measurement). */
 MCT_API int mct_kernel_eval_many(mct_kernel_t kernel, int n, const double *F, double *out, float *device_ms);
+/* A kernel handle must outlive every equation created on it (the equation uses the kernel's stream and scratch). */
 MCT_API int mct_kernel_destroy(mct_kernel_t kernel);
 
 /* ---- TimeDoublingSolver: plug-in point #1, `solve(equation, solver)`  src/Solvers.jl:42-46 ---- */
@@ -138,6 +139,16 @@ MCT_API int mct_equation_solve_batch(int n, mct_equation_t *eqs, int *status, lo
  *                                     collective call); everything else is replicated, so all ranks hold the solution. */
 MCT_API int mct_equation_shard_prepare(mct_equation_t eq, int rank, int world, unsigned char *handle_out /* 64 bytes */);
 MCT_API int mct_equation_shard_connect(mct_equation_t eq, const unsigned char *handles /* [world][64] */);
+
+/* get_F(sol, its, iks) / get_K (src/HelperFunctions.jl:169-210) on the device-resident solution: gathers
+ * F[times[i]][dofs[j]] into F_out[n_times][n_dofs] on the device and copies only that.  times == NULL: all nt output
+ * times (n_times ignored); dofs == NULL: all dof entries.  t_out (n_times), F_out, K_out may each be NULL. */
+MCT_API int mct_equation_download_slice(mct_equation_t eq, long n_times, const long *times, int n_dofs, const int *dofs,
+                                double *t_out, double *F_out, double *K_out);
+/* find_relaxation_time(t, F(k); threshold, mode) (src/RelaxationTime.jl:14-39) for n_k wavenumbers of a solved
+ * single-valued equation: the columns are gathered on the device (8 nt n_k bytes cross PCIe instead of the whole
+ * trajectory); the O(nt) search and interpolation run on the host as in the reference.  mode 0 = :log, 1 = :lin. */
+MCT_API int mct_equation_relaxation_times(mct_equation_t eq, int n_k, const int *ik, double threshold, int mode, double *tau_out);
 
 /* MSDModeCouplingKernel(rho, kBT, m, k_array, S, sol, taggedsol) (src/Kernels/ModeCouplingKernels.jl:552-570) and
  * solve(MemoryEquation(alpha, beta, gamma, delta, MSD0, dMSD0, kernel), TimeDoublingSolver) for it

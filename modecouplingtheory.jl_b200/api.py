@@ -53,7 +53,7 @@ EXPORTS = [
     "mct_sc3d_tagged_create", "mct_sc3d_tagged_create_from_sk", "mct_sc3d_tagged_create_from_equation", "mct_mc3d_create",
     "mct_ddim_create", "mct_kernel_eval", "mct_kernel_eval_many", "mct_kernel_destroy", "mct_td_output_len", "mct_td_solve",
     "mct_equation_create", "mct_equation_solve", "mct_equation_download", "mct_equation_destroy", "mct_equation_solve_batch", "mct_equation_shard_prepare", "mct_equation_shard_connect",
-    "mct_steady_state", "mct_msd3d_solve",
+    "mct_steady_state", "mct_msd3d_solve", "mct_equation_download_slice", "mct_equation_relaxation_times",
 ]
 
 
@@ -410,13 +410,15 @@ class TimeDoublingSolver:
 
 
 class _DeviceEquation:
-    def __init__(self, q):
+    def __init__(self, q, kernel=None):
         self._q = q
+        self._kernel = kernel      # the equation handle refers to the kernel handle: keep it alive as long as the equation
 
     def close(self):
         if self._q is not None and _lib is not None:
             _lib.mct_equation_destroy(self._q)
             self._q = None
+        self._kernel = None
 
     def __del__(self):
         try:
@@ -455,7 +457,7 @@ def _create_equation(equation, solver):
     c = equation._c_coeffs()
     o = solver._c_opts()
     _check(L.mct_equation_create(C.byref(q), equation.kernel._h, C.byref(c), _p(equation.F0), _p(equation.dF0), C.byref(o)))
-    return _DeviceEquation(q)
+    return _DeviceEquation(q, equation.kernel)
 
 
 def _download(dev_eq, solver, dof, keep_device):
@@ -516,6 +518,35 @@ def download_solution(dev_eq, solver, dof):
     return _download(dev_eq, solver, dof, False)
 
 
+def download_slice(dev_eq, dof, times=None, dofs=None, want_K=True):
+    """get_F(sol, its, iks) / get_K on a device-resident solution (src/HelperFunctions.jl:169-210): only the requested
+    [times, dofs] slice crosses PCIe.  Returns (t, F, K) with F, K of shape [len(times), len(dofs)]."""
+    L = load_library()
+    nt = C.c_long(0)
+    ti = None if times is None else np.ascontiguousarray(times, dtype=np.int64)
+    di = None if dofs is None else np.ascontiguousarray(dofs, dtype=np.int32)
+    if ti is None:
+        raise ValueError("pass the time indices (use download_solution for whole trajectories)")
+    n_t, n_d = len(ti), (dof if di is None else len(di))
+    t = np.empty(n_t); F = np.empty((n_t, n_d)); K = np.empty((n_t, n_d)) if want_K else None
+    _check(L.mct_equation_download_slice(dev_eq._q, C.c_long(n_t), ti.ctypes.data_as(C.POINTER(C.c_long)), n_d,
+                                         None if di is None else di.ctypes.data_as(C.POINTER(C.c_int)),
+                                         _p(t), _p(F), None if K is None else _p(K)))
+    return t, F, K
+
+
+def relaxation_times(dev_eq, ik, threshold=np.exp(-1), mode="log"):
+    """find_relaxation_time(t, F(k_ik); threshold, mode) for the wavenumbers `ik` of a device-resident solution."""
+    if mode not in ("log", "lin"):
+        raise ValueError(f"the mode ':{mode}' is not know. it must be either :lin, :log.")
+    L = load_library()
+    idx = np.ascontiguousarray(np.atleast_1d(ik), dtype=np.int32)
+    tau = np.empty(len(idx))
+    _check(L.mct_equation_relaxation_times(dev_eq._q, len(idx), idx.ctypes.data_as(C.POINTER(C.c_int)), C.c_double(threshold),
+                                           0 if mode == "log" else 1, _p(tau)))
+    return tau
+
+
 def solve_into(equation, solver, t, F, K):
     """solve(equation, solver) through the one-call C entry point `mct_td_solve` with caller-owned HOST buffers
     (t[nt], F[nt, dof], K[nt, dof]) -- what the Julia glue ccalls."""
@@ -544,7 +575,11 @@ def solve_batch(equations, solver=None, download=True):
     if rc not in (MCT_OK, MCT_NOT_CONVERGED):
         _check(rc)
     sols = []
-    if download:
+    if isinstance(download, dict):            # {"times": [...], "dofs": [...]}: only that slice of every solution comes back
+        for d, e in zip(devs, equations):
+            t, F, K = download_slice(d, e.kernel.dof, download.get("times"), download.get("dofs"), download.get("K", True))
+            sols.append(MemoryEquationSolution(t, F, K, solver))
+    elif download:
         for d, e in zip(devs, equations):
             sols.append(_download(d, solver, e.kernel.dof, False))
     for d in devs:

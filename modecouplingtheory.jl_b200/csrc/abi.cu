@@ -857,6 +857,80 @@ int mct_equation_download(mct_equation_t q, double *t_out, double *F_out, double
     return MCT_OK;
 }
 
+static void output_times(const mct_equation_s *q, std::vector<double> &t) {
+    // t = dt/(4N) * it, exactly as allocate_results! forms it (src/TimeDoublingSolver.jl:431-434)
+    const int N = q->opts.N;
+    t.clear();
+    t.push_back(0.0);
+    double Dt = q->opts.dt;
+    const double d0 = Dt / (4.0 * N);
+    for (int it = 1; it <= 2 * N; it++) t.push_back(d0 * it);
+    for (int b = 0; b < q->nblocks; b++, Dt *= 2.0) {
+        const double dl = Dt / (4.0 * N);
+        for (int it = 2 * N + 1; it <= 4 * N; it++) t.push_back(dl * it);
+    }
+}
+
+int mct_equation_download_slice(mct_equation_t q, long n_times, const long *times, int n_dofs, const int *dofs,
+                                double *t_out, double *F_out, double *K_out) {
+    MCT_REQUIRE(q && q->mode == 0, MCT_BAD_ARGUMENT, "NULL equation");
+    const int dof = q->Nk * q->ns * q->ns;
+    if (!times) n_times = q->nt;
+    if (!dofs) n_dofs = dof;
+    MCT_REQUIRE(n_times >= 1 && n_dofs >= 1, MCT_BAD_ARGUMENT, "empty slice");
+    for (long i = 0; times && i < n_times; i++) MCT_REQUIRE(times[i] >= 0 && times[i] < q->nt, MCT_BAD_ARGUMENT, "time index out of range");
+    for (int j = 0; dofs && j < n_dofs; j++) MCT_REQUIRE(dofs[j] >= 0 && dofs[j] < dof, MCT_BAD_ARGUMENT, "wavenumber index out of range");
+    mct_kernel_t h = q->kernel;
+    MCT_CUDA(cudaSetDevice(h->device));
+    const size_t n = (size_t)n_times * n_dofs;
+    const size_t idx_doubles = (size_t)(times ? n_times : 0) + (size_t)(dofs ? (n_dofs + 1) / 2 : 0);
+    int rc = ensure_io(h, n + idx_doubles + 2);
+    if (rc) return rc;
+    long *d_times = times ? (long *)(h->d_io + n) : nullptr;
+    int *d_dofs = dofs ? (int *)(h->d_io + n + (times ? n_times : 0)) : nullptr;
+    if (times) MCT_CUDA(cudaMemcpyAsync(d_times, times, n_times * sizeof(long), cudaMemcpyHostToDevice, h->stream));
+    if (dofs) MCT_CUDA(cudaMemcpyAsync(d_dofs, dofs, n_dofs * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    for (int pass = 0; pass < 2; pass++) {
+        double *out = pass ? K_out : F_out;
+        if (!out) continue;
+        rc = gather_slice_launch(pass ? q->d_K : q->d_F, dof, d_times, n_times, d_dofs, n_dofs, h->d_io, h->stream);
+        if (rc) return rc;
+        MCT_CUDA(cudaMemcpyAsync(out, h->d_io, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        MCT_CUDA(cudaStreamSynchronize(h->stream));
+    }
+    if (t_out) {
+        std::vector<double> t;
+        output_times(q, t);
+        for (long i = 0; i < n_times; i++) t_out[i] = t[times ? times[i] : i];
+    }
+    return MCT_OK;
+}
+
+int mct_equation_relaxation_times(mct_equation_t q, int n_k, const int *ik, double threshold, int mode, double *tau_out) {
+    MCT_REQUIRE(q && ik && tau_out && n_k >= 1, MCT_BAD_ARGUMENT, "NULL argument to mct_equation_relaxation_times");
+    MCT_REQUIRE(mode == 0 || mode == 1, MCT_BAD_ARGUMENT, "the mode is not known. it must be either :lin (1), :log (0).");
+    std::vector<double> F((size_t)q->nt * n_k), t;
+    int rc = mct_equation_download_slice(q, 0, nullptr, n_k, ik, nullptr, F.data(), nullptr);
+    if (rc) return rc;
+    output_times(q, t);
+    for (int j = 0; j < n_k; j++) {                                   // src/RelaxationTime.jl:14-39 per requested wavenumber
+        double tau = INFINITY;
+        const double f0 = F[j];
+        for (long it = 0; it < q->nt; it++) {
+            const double y0 = F[(size_t)it * n_k + j] / f0;
+            if (y0 > threshold) continue;
+            if (it == 0) { tau = 0.0; break; }
+            const double y1 = F[(size_t)(it - 1) * n_k + j] / f0, y = threshold;
+            const double x0 = mode == 0 ? std::log(t[it]) : t[it], x1 = mode == 0 ? std::log(t[it - 1]) : t[it - 1];
+            const double x = ((y - y0) * (x1 - x0) + x0 * (y1 - y0)) / (y1 - y0);
+            tau = mode == 0 ? std::exp(x) : x;
+            break;
+        }
+        tau_out[j] = tau;
+    }
+    return MCT_OK;
+}
+
 int mct_td_solve(mct_kernel_t h, const mct_coeffs *c, const double *F0, const double *dF0, const mct_td_options *o,
                  double *t_out, double *F_out, double *K_out, long *kernel_evals) {
     mct_equation_t q = nullptr;

@@ -131,7 +131,27 @@ __global__ void msd_scalar_td_kernel(const MsdParams P) {
 #undef KINT
 }
 
+__global__ void gather_slice_kernel(const double *src, int dof, const long *times, long n_times, const int *dofs, int n_dofs,
+                                    double *dst) {
+    const size_t n = (size_t)n_times * n_dofs;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const long ti = (long)(i / n_dofs);
+        const int dj = (int)(i - (size_t)ti * n_dofs);
+        dst[i] = src[(size_t)(times ? times[ti] : ti) * dof + (dofs ? dofs[dj] : dj)];
+    }
+}
+
 }  // namespace
+
+int gather_slice_launch(const double *src, int dof, const long *d_times, long n_times, const int *d_dofs, int n_dofs,
+                        double *dst, cudaStream_t stream) {
+    const size_t n = (size_t)n_times * n_dofs;
+    const int blocks = (int)std::min<size_t>((n + kThreads - 1) / kThreads, 148 * 8);
+    gather_slice_kernel<<<std::max(blocks, 1), kThreads, 0, stream>>>(src, dof, d_times, n_times, d_dofs, n_dofs, dst);
+    count_launch();
+    MCT_CUDA(cudaGetLastError());
+    return MCT_OK;
+}
 
 int msd3d_launch(const MsdParams &P, cudaStream_t stream) {
     const int blocks = (int)std::min<long>(P.nt, 148 * 8);

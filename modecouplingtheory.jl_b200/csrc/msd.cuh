@@ -21,4 +21,9 @@ struct MsdParams {
 
 int msd3d_launch(const MsdParams &P, cudaStream_t stream);
 
+// dst[i][j] = src[times[i]][dofs[j]] of a device trajectory [nt][dof]; NULL index lists mean "all"  (get_F(sol, its, iks),
+// src/HelperFunctions.jl:169-210 -- SURVEY 8f-3: only the requested slice crosses PCIe)
+int gather_slice_launch(const double *src, int dof, const long *d_times, long n_times, const int *d_dofs, int n_dofs,
+                        double *dst, cudaStream_t stream);
+
 }  // namespace mct

@@ -44,9 +44,11 @@ def gather(local_indices, local_values, n_points, world, dist=None):
     return out
 
 
-def run_sweep(pkg, etas, Nk, device, solver_kwargs=None, batch=None, observable=None):
+def run_sweep(pkg, etas, Nk, device, solver_kwargs=None, batch=None, observable=None, download=True):
     """Solve the hard-sphere MCT equation at every packing fraction in `etas` on one GPU, `batch` equations per
-    persistent launch.  Returns (values [len(etas), w], total kernel evaluations, device milliseconds)."""
+    persistent launch.  `download` is passed to solve_batch: True = whole trajectories, a dict(times=, dofs=) = only that
+    slice (the observable then sees the sliced F, K).  Returns (values [len(etas), w], total kernel evaluations, device
+    milliseconds)."""
     sf = pkg.structure_factors
     solver_kwargs = dict(solver_kwargs or {})
     solver_kwargs.setdefault("max_iterations", 10 ** 6)
@@ -60,7 +62,7 @@ def run_sweep(pkg, etas, Nk, device, solver_kwargs=None, batch=None, observable=
             Sk = sf.percus_yevick_sk(k, eta)
             kern = pkg.ModeCouplingKernel(6 * eta / np.pi, 1.0, 1.0, k, Sk, device=device)
             eqs.append(pkg.MemoryEquation(0.0, 1.0, k ** 2 / Sk, 0.0, Sk, np.zeros(Nk), kern))
-        sols, status, evals, ms = pkg.solve_batch(eqs, pkg.TimeDoublingSolver(**solver_kwargs))
+        sols, status, evals, ms = pkg.solve_batch(eqs, pkg.TimeDoublingSolver(**solver_kwargs), download=download)
         if any(status):
             raise pkg.DomainError(f"sweep: solver status {status}")
         values += [observable(s) for s in sols]

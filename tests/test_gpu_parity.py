@@ -268,3 +268,32 @@ def test_steady_state_below_critical_point_is_zero():
     p = P.hard_spheres(100, 0.50)
     sol = pkg.solve_steady_state(p["k"] ** 2 / p["Sk"], p["Sk"], gpu_kernel(p), tolerance=1e-10)
     assert sol.F.sum() < 1e-7
+
+
+def test_slice_download_and_relaxation_times_match_the_full_trajectory():
+    """get_F(sol, its, iks) and find_relaxation_time on the device-resident solution must give exactly what
+    the whole downloaded trajectory gives (src/HelperFunctions.jl:169-210, src/RelaxationTime.jl:14-39)."""
+    p = P.hard_spheres(100, 0.51)
+    sol, solver = gpu_solve(p, P.overdamped(p), N=8, dt=1e-8, t_max=1e6, tolerance=1e-10)
+    nt = sol.F.shape[0]
+    times = np.array([0, 1, 17, nt // 2, nt - 1])
+    dofs = np.array([0, 18, 19, 99])
+    t, F, K = pkg.api.download_slice(sol._equation, 100, times, dofs)
+    assert np.array_equal(t, sol.t[times])
+    assert np.array_equal(F, sol.F[np.ix_(times, dofs)])
+    assert np.array_equal(K, sol.K[np.ix_(times, dofs)])
+    t, F, K = pkg.api.download_slice(sol._equation, 100, [nt - 1], None, want_K=False)        # f(k) at the last time
+    assert K is None and np.array_equal(F[0], sol.F[-1])
+    for mode in ("log", "lin"):
+        tau = pkg.api.relaxation_times(sol._equation, dofs, mode=mode)
+        host = [pkg.find_relaxation_time(sol.t, sol.F[:, ik], mode=mode) for ik in dofs]
+        assert np.allclose(tau, host, rtol=1e-14, atol=0)
+    assert np.isinf(pkg.api.relaxation_times(sol._equation, [18], threshold=-1.0)[0])           # never crossed
+    with pytest.raises(Exception):
+        pkg.api.download_slice(sol._equation, 100, [nt], [0])
+    # batch solve that returns only the slice (what the packing-fraction sweep needs)
+    eq = pkg.MemoryEquation(0.0, 1.0, p["k"] ** 2 / p["Sk"], 0.0, p["Sk"], np.zeros(100), gpu_kernel(p))
+    sols, status, _, _ = pkg.solve_batch([eq], pkg.TimeDoublingSolver(N=8, dt=1e-8, t_max=1e6, tolerance=1e-10),
+                                         download=dict(times=[0, nt - 1], dofs=[18], K=False))
+    assert status == [0] and sols[0].F.shape == (2, 1)
+    assert np.allclose(sols[0].F[:, 0], sol.F[[0, nt - 1], 18], rtol=0, atol=1e-10)
