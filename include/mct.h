@@ -140,6 +140,21 @@ MCT_API int mct_equation_solve_batch(int n, mct_equation_t *eqs, int *status, lo
 MCT_API int mct_equation_shard_prepare(mct_equation_t eq, int rank, int world, unsigned char *handle_out /* 64 bytes */);
 MCT_API int mct_equation_shard_connect(mct_equation_t eq, const unsigned char *handles /* [world][64] */);
 
+/* TaggedMultiComponentModeCouplingKernel(s, rho, kBT, m, k_array, S, sol) (src/Kernels/MultiComponentKernels.jl:268-333)
+ * chained on the device-resident solution of a multi-component equation.  fill_A! (:335-370) is
+ * A_m[iq,ip] = V_m[iq,ip] Fs[ip] G(iq,t) with the species weight G(q,t) = sum_ab C_q[s,a] C_q[s,b] F_ab(q,t): G is
+ * contracted once on the device from the mixture trajectory and the kernel then is a tagged single-component kernel
+ * (same persistent solver).  s is 0-based; rho_all = sum(rho), m_s = m[s]. */
+MCT_API int mct_mc3d_tagged_create_from_equation(mct_kernel_t *out, int s, double rho_all, double kBT, double m_s,
+                                         mct_equation_t collective);
+/* MSDMultiComponentModeCouplingKernel(s, ...) (:400-486) + the scalar solve, like mct_msd3d_solve.  `collective` is the
+ * solved mixture equation, `tagged` the solved tagged-particle equation of species s (0-based).
+ * full_species_sum = 0 reproduces the reference: `Ns = length(Fs[1])` (:477) is 1 there, so its species sum only visits
+ * alpha = beta = 1 and the golden test/test_MCMCT.jl:226 is that number; 1 evaluates the documented sum over all pairs. */
+MCT_API int mct_msd_mc3d_solve(mct_equation_t collective, mct_equation_t tagged, int s, int full_species_sum, double rho_all,
+                       double kBT, double m_s, double alpha, double beta, double gamma, double delta, double MSD0, double dMSD0,
+                       double *t_out, double *msd_out, double *K_out, long *kernel_evals);
+
 /* get_F(sol, its, iks) / get_K (src/HelperFunctions.jl:169-210) on the device-resident solution: gathers
  * F[times[i]][dofs[j]] into F_out[n_times][n_dofs] on the device and copies only that.  times == NULL: all nt output
  * times (n_times ignored); dofs == NULL: all dof entries.  t_out (n_times), F_out, K_out may each be NULL. */

@@ -8,7 +8,8 @@ from . import api, structure_factors, sweep  # noqa: F401
 from .api import (  # noqa: F401
     DomainError, MCTDeviceError, MemoryEquation, MemoryEquationSolution, MemoryKernel, ModeCouplingKernel,
     MultiComponentModeCouplingKernel, dDimModeCouplingKernel, ddim_tables,
-    TaggedModeCouplingKernel, MSDModeCouplingKernel, TimeDoublingSolver, device_count, launch_count, evaluate_kernel, evaluate_kernel_, evaluate_kernel_many,
+    TaggedModeCouplingKernel, MSDModeCouplingKernel, TaggedMultiComponentModeCouplingKernel,
+    MSDMultiComponentModeCouplingKernel, TimeDoublingSolver, device_count, launch_count, evaluate_kernel, evaluate_kernel_, evaluate_kernel_many,
     find_relaxation_time, get_F, get_K, get_t, library_path, load_library, solve, solve_batch, solve_steady_state,
     vertex_tables, EXPORTS,
 )

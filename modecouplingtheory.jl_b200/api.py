@@ -54,6 +54,7 @@ EXPORTS = [
     "mct_ddim_create", "mct_kernel_eval", "mct_kernel_eval_many", "mct_kernel_destroy", "mct_td_output_len", "mct_td_solve",
     "mct_equation_create", "mct_equation_solve", "mct_equation_download", "mct_equation_destroy", "mct_equation_solve_batch", "mct_equation_shard_prepare", "mct_equation_shard_connect",
     "mct_steady_state", "mct_msd3d_solve", "mct_equation_download_slice", "mct_equation_relaxation_times",
+    "mct_mc3d_tagged_create_from_equation", "mct_msd_mc3d_solve",
 ]
 
 
@@ -214,12 +215,18 @@ class MSDKernel:
     Ns = 1
     dof = 1
 
-    def __init__(self, rho, kBT, m, k_array, Sk, sol, taggedsol):
+    def __init__(self, rho, kBT, m, k_array, Sk, sol, taggedsol, species=None, full_species_sum=False):
         if getattr(sol, "_equation", None) is None or getattr(taggedsol, "_equation", None) is None:
             raise MCTDeviceError("MSDModeCouplingKernel needs the device-resident solutions (solve(..., keep_device=True))")
-        self.rho, self.kBT, self.m = float(rho), float(kBT), float(m)
+        self.species = species                    # None: single component; else 0-based species of a mixture
+        self.full_species_sum = bool(full_species_sum)
+        if species is None:
+            self.rho, self.kBT, self.m = float(rho), float(kBT), float(m)
+            self.Sk = _arr(Sk)
+        else:
+            self.rho, self.kBT, self.m = float(np.sum(rho)), float(kBT), float(np.asarray(m, dtype=np.float64)[species])
+            self.Sk = None
         self.k = _arr(k_array)
-        self.Sk = _arr(Sk)
         self.sol, self.taggedsol = sol, taggedsol
 
 
@@ -227,6 +234,34 @@ def MSDModeCouplingKernel(rho, kBT, m, k_array, Sk, sol, taggedsol, dims=3):
     if dims != 3:
         raise NotImplementedError("dDimMSDModeCouplingKernel is not implemented on the device yet")
     return MSDKernel(rho, kBT, m, k_array, Sk, sol, taggedsol)
+
+
+def TaggedMultiComponentModeCouplingKernel(s, rho, kBT, m, k_array, Sk, sol, dims=3):
+    """TaggedMultiComponentModeCouplingKernel(s, ρ, kBT, m, k_array, Sₖ, sol; dims=3) --
+    src/Kernels/MultiComponentKernels.jl:268-333.  `s` is the reference's 1-based species index; `sol` must be the
+    device-resident solution of the multi-component equation (the species weight is contracted from it on the device)."""
+    if dims != 3:
+        raise NotImplementedError("MSD is not implemented for dimentions other than 3")
+    if getattr(sol, "_equation", None) is None:
+        raise MCTDeviceError("TaggedMultiComponentModeCouplingKernel needs the device-resident mixture solution")
+    L = load_library()
+    m = np.asarray(m, dtype=np.float64)
+    if not (1 <= s <= len(m)):
+        raise AssertionError("species index out of range")
+    h = C.c_void_p()
+    _check(L.mct_mc3d_tagged_create_from_equation(C.byref(h), int(s) - 1, C.c_double(float(np.sum(rho))), C.c_double(kBT),
+                                                  C.c_double(float(m[s - 1])), sol._equation._q))
+    return MemoryKernel(h, len(k_array), 1, sol._equation._kernel.device, keep=(sol._equation,))
+
+
+def MSDMultiComponentModeCouplingKernel(s, rho, kBT, m, k_array, Sk, sol, taggedsol, dims=3, full_species_sum=False):
+    """MSDMultiComponentModeCouplingKernel(s, ρ, kBT, m, k_array, Sₖ, sol, taggedsol) -- MultiComponentKernels.jl:400-468;
+    `taggedsol` must come from a TaggedMultiComponentModeCouplingKernel of the same species.  The reference's species
+    sum only visits the first species (`Ns = length(Fs[1])` is 1, :477); that behaviour -- and its golden -- is the
+    default, full_species_sum=True evaluates the documented sum over all pairs."""
+    if dims != 3:
+        raise NotImplementedError("MSD is not implemented for dimentions other than 3")
+    return MSDKernel(rho, kBT, m, k_array, Sk, sol, taggedsol, species=int(s) - 1, full_species_sum=full_species_sum)
 
 
 def _solve_msd(equation, solver):
@@ -242,10 +277,15 @@ def _solve_msd(equation, solver):
     t = np.empty(nt); F = np.empty(nt); K = np.empty(nt)
     evals = C.c_long(0)
     delta = 0.0 if equation.delta is None else float(equation.delta[0])
-    rc = L.mct_msd3d_solve(q._q, kern.taggedsol._equation._q, C.c_double(kern.rho), C.c_double(kern.kBT), C.c_double(kern.m),
-                           _p(kern.Sk), C.c_double(equation.coeffs["alpha"]), C.c_double(equation.coeffs["beta"]),
-                           C.c_double(equation.coeffs["gamma"]), C.c_double(delta), C.c_double(float(equation.F0[0])),
-                           C.c_double(float(equation.dF0[0])), _p(t), _p(F), _p(K), C.byref(evals))
+    tail = (C.c_double(equation.coeffs["alpha"]), C.c_double(equation.coeffs["beta"]), C.c_double(equation.coeffs["gamma"]),
+            C.c_double(delta), C.c_double(float(equation.F0[0])), C.c_double(float(equation.dF0[0])), _p(t), _p(F), _p(K),
+            C.byref(evals))
+    if kern.species is None:
+        rc = L.mct_msd3d_solve(q._q, kern.taggedsol._equation._q, C.c_double(kern.rho), C.c_double(kern.kBT), C.c_double(kern.m),
+                               _p(kern.Sk), *tail)
+    else:
+        rc = L.mct_msd_mc3d_solve(q._q, kern.taggedsol._equation._q, int(kern.species), int(kern.full_species_sum),
+                                  C.c_double(kern.rho), C.c_double(kern.kBT), C.c_double(kern.m), *tail)
     solver.kernel_evals = evals.value
     _check(rc)
     return MemoryEquationSolution(t, F, K, solver)

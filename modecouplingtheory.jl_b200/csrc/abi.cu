@@ -590,6 +590,41 @@ int mct_sc3d_tagged_create_from_equation(mct_kernel_t *out, int Nk, double rho, 
     return MCT_OK;
 }
 
+int mct_mc3d_tagged_create_from_equation(mct_kernel_t *out, int s, double rho_all, double kBT, double m_s, mct_equation_t collective) {
+    MCT_REQUIRE(out && collective && collective->solved && collective->mode == 0 && collective->d_gws && collective->kernel &&
+                    collective->kernel->type == K_MC3D,
+                MCT_BAD_ARGUMENT, "a solved multi-component equation is needed to chain a tagged kernel on it");
+    mct_kernel_t hc = collective->kernel;
+    const int Nk = hc->Nk, ns = hc->Ns;
+    MCT_REQUIRE(s >= 0 && s < ns, MCT_BAD_ARGUMENT, "species index out of range (0-based)");
+    MCT_CUDA(cudaSetDevice(hc->device));
+    std::vector<double> k(Nk);
+    MCT_CUDA(cudaMemcpy(k.data(), hc->d_k, Nk * sizeof(double), cudaMemcpyDeviceToHost));
+    int rc = new_handle(out, K_TAGGED3D, hc->device, Nk, k.data());
+    if (rc) return rc;
+    mct_kernel_t h = *out;
+    // vertex tables of the constructor (src/Kernels/MultiComponentKernels.jl:297-310); the c's are in the species weight
+    const double dk = k[1] - k[0], pi = 3.14159265358979323846;
+    const double pref = kBT * (dk * dk) * rho_all / (4 * m_s * ((2 * pi) * (2 * pi)));
+    std::vector<double> V1((size_t)Nk * Nk), V2(V1.size()), V3(V1.size());
+    for (int ip = 0; ip < Nk; ip++)
+        for (int iq = 0; iq < Nk; iq++) {
+            const double p = k[ip], q = k[iq], d2 = q * q - p * p;
+            const size_t w = (size_t)iq + (size_t)Nk * ip;
+            V1[w] = pref * p * q; V2[w] = pref * p * q * (d2 * d2); V3[w] = pref * 2 * p * q * d2;
+        }
+    rc = upload_tables(h, V1.data(), V2.data(), V3.data());
+    if (!rc) {
+        h->nt = collective->nt; h->owns_Fc = true;
+        cudaError_t e = cudaMalloc(&h->d_Fc, (size_t)h->nt * Nk * sizeof(double));
+        if (e != cudaSuccess) rc = cuda_fail(e, "mct_mc3d_tagged_create_from_equation", __FILE__, __LINE__);
+    }
+    if (!rc) rc = mc_species_weight_launch(collective->d_F, hc->d_C, Nk, ns, s, h->nt, h->d_Fc, h->stream);
+    if (!rc) { cudaError_t e = cudaStreamSynchronize(h->stream); if (e != cudaSuccess) rc = cuda_fail(e, "species weight", __FILE__, __LINE__); }
+    if (rc) { mct_kernel_destroy(h); *out = nullptr; }
+    return rc;
+}
+
 int mct_mc3d_create(mct_kernel_t *out, int device, int Nk, int Ns, const double *k_array, const double *Cblocks, const double *prefactor) {
     MCT_REQUIRE(Ns >= 1 && Ns <= kNsMax, MCT_UNSUPPORTED, "the device supports 1 <= Ns <= 4 species");
     MCT_REQUIRE(Cblocks && prefactor, MCT_BAD_ARGUMENT, "NULL argument to mct_mc3d_create");
@@ -975,25 +1010,20 @@ int mct_equation_shard_connect(mct_equation_t q, const unsigned char *handles) {
     return MCT_OK;
 }
 
-int mct_msd3d_solve(mct_equation_t collective, mct_equation_t tagged, double rho, double kBT, double m, const double *Sk,
-                    double alpha, double beta, double gamma, double delta, double MSD0, double dMSD0,
-                    double *t_out, double *msd_out, double *K_out, long *kernel_evals) {
-    MCT_REQUIRE(collective && tagged && Sk && t_out && msd_out && K_out, MCT_BAD_ARGUMENT, "NULL argument to mct_msd3d_solve");
-    MCT_REQUIRE(collective->solved && tagged->solved, MCT_BAD_ARGUMENT, "both equations must have been solved on the device");
-    MCT_REQUIRE(collective->ns == 1 && tagged->ns == 1 && !collective->d_gws && !tagged->d_gws, MCT_UNSUPPORTED,
-                "the MSD kernel is implemented for single-component solutions");
-    MCT_REQUIRE(collective->Nk == tagged->Nk && collective->nt == tagged->nt && collective->opts.N == tagged->opts.N &&
-                    collective->opts.dt == tagged->opts.dt,
-                MCT_BAD_ARGUMENT, "the two solutions must share the wavenumber grid and the time grid (tDict lookup)");
-    MCT_REQUIRE(collective->kernel->device == tagged->kernel->device, MCT_BAD_ARGUMENT, "the two solutions live on different devices");
+// Shared by the single- and multi-component MSD entry points: Fc = trajectory the tagged trajectory is contracted with
+// (collective F with weights q^4 c^2, or the species weight G with weights q^4).
+static int msd_solve_common(mct_equation_t tagged, const double *d_Fc, const double *Sk, const double *d_Cmix, int ns, int sp,
+                            int species_terms, double rho, double kBT, double m,
+                            double alpha, double beta, double gamma, double delta, double MSD0, double dMSD0,
+                            double *t_out, double *msd_out, double *K_out, long *kernel_evals) {
     MCT_REQUIRE(alpha != 0.0 || beta != 0.0, MCT_BAD_ARGUMENT, "alpha and beta are both zero");
-    mct_kernel_t h = collective->kernel;
-    const int Nk = collective->Nk;
-    const long nt = collective->nt;
+    mct_kernel_t h = tagged->kernel;
+    const int Nk = tagged->Nk;
+    const long nt = tagged->nt;
     MCT_CUDA(cudaSetDevice(h->device));
-    std::vector<double> kh(Nk), ck(Nk);
+    std::vector<double> kh(Nk), ck(Nk, 0.0);
     MCT_CUDA(cudaMemcpy(kh.data(), h->d_k, Nk * sizeof(double), cudaMemcpyDeviceToHost));
-    for (int i = 0; i < Nk; i++) ck[i] = (Sk[i] - 1.0) / (rho * Sk[i]);             // ModeCouplingKernels.jl:566
+    for (int i = 0; Sk && i < Nk; i++) ck[i] = (Sk[i] - 1.0) / (rho * Sk[i]);       // ModeCouplingKernels.jl:566
     const double dk = kh[1] - kh[0];
     const double pi = 3.14159265358979323846;
     double *d = nullptr;                                  // Ck [Nk], Ktab [nt], t/F/K out [3 nt], status, evals
@@ -1002,11 +1032,12 @@ int mct_msd3d_solve(mct_equation_t collective, mct_equation_t tagged, double rho
     if (e == cudaSuccess) e = cudaMemset(d + Nk + 4 * nt, 0, 4 * sizeof(double));
     if (e != cudaSuccess) { cudaFree(d); return cuda_fail(e, "mct_msd3d_solve setup", __FILE__, __LINE__); }
     MsdParams P{};
-    P.Nk = Nk; P.N = collective->opts.N; P.nblocks = collective->nblocks; P.nt = nt;
-    P.dt0 = collective->opts.dt; P.tol = collective->opts.tolerance; P.max_iter = collective->opts.max_iterations;
+    P.Nk = Nk; P.N = tagged->opts.N; P.nblocks = tagged->nblocks; P.nt = nt;
+    P.dt0 = tagged->opts.dt; P.tol = tagged->opts.tolerance; P.max_iter = tagged->opts.max_iterations;
     P.alpha = alpha; P.beta = beta; P.gamma = gamma; P.delta = delta; P.F0 = MSD0; P.dF0 = dMSD0;
-    P.scale = dk * rho * kBT / (6.0 * (pi * pi) * m);                               // :583
-    P.kvec = h->d_k; P.Ck = d; P.Fc = collective->d_F; P.Fs = tagged->d_F;
+    P.scale = dk * rho * kBT / (6.0 * (pi * pi) * m);                               // :583 / MultiComponentKernels.jl:486
+    P.kvec = h->d_k; P.Ck = d; P.Fc = d_Fc; P.Fs = tagged->d_F;
+    P.Cmix = d_Cmix; P.ns = ns; P.s = sp; P.species_terms = species_terms;
     P.Ktab = d + Nk; P.t_out = d + Nk + nt; P.F_out = d + Nk + 2 * nt; P.K_out = d + Nk + 3 * nt;
     P.status = (int *)(d + Nk + 4 * nt); P.kernel_evals = (long long *)(d + Nk + 4 * nt + 2);
     int rc = msd3d_launch(P, h->stream);
@@ -1027,6 +1058,37 @@ int mct_msd3d_solve(mct_equation_t collective, mct_equation_t tagged, double rho
     }
     cudaFree(d);
     return rc;
+}
+
+int mct_msd3d_solve(mct_equation_t collective, mct_equation_t tagged, double rho, double kBT, double m, const double *Sk,
+                    double alpha, double beta, double gamma, double delta, double MSD0, double dMSD0,
+                    double *t_out, double *msd_out, double *K_out, long *kernel_evals) {
+    MCT_REQUIRE(collective && tagged && Sk && t_out && msd_out && K_out, MCT_BAD_ARGUMENT, "NULL argument to mct_msd3d_solve");
+    MCT_REQUIRE(collective->solved && tagged->solved, MCT_BAD_ARGUMENT, "both equations must have been solved on the device");
+    MCT_REQUIRE(collective->ns == 1 && tagged->ns == 1 && !collective->d_gws && !tagged->d_gws, MCT_UNSUPPORTED,
+                "mct_msd3d_solve takes single-component solutions (mixtures: mct_msd_mc3d_solve)");
+    MCT_REQUIRE(collective->Nk == tagged->Nk && collective->nt == tagged->nt && collective->opts.N == tagged->opts.N &&
+                    collective->opts.dt == tagged->opts.dt,
+                MCT_BAD_ARGUMENT, "the two solutions must share the wavenumber grid and the time grid (tDict lookup)");
+    MCT_REQUIRE(collective->kernel->device == tagged->kernel->device, MCT_BAD_ARGUMENT, "the two solutions live on different devices");
+    return msd_solve_common(tagged, collective->d_F, Sk, nullptr, 1, 0, 1, rho, kBT, m, alpha, beta, gamma, delta, MSD0, dMSD0, t_out,
+                            msd_out, K_out, kernel_evals);
+}
+
+int mct_msd_mc3d_solve(mct_equation_t collective, mct_equation_t tagged, int s, int full_species_sum, double rho_all, double kBT,
+                       double m_s, double alpha, double beta, double gamma, double delta, double MSD0, double dMSD0,
+                       double *t_out, double *msd_out, double *K_out, long *kernel_evals) {
+    MCT_REQUIRE(collective && tagged && t_out && msd_out && K_out, MCT_BAD_ARGUMENT, "NULL argument to mct_msd_mc3d_solve");
+    MCT_REQUIRE(collective->solved && collective->mode == 0 && collective->d_gws && collective->kernel->type == K_MC3D,
+                MCT_BAD_ARGUMENT, "a solved multi-component equation is needed");
+    MCT_REQUIRE(tagged->solved && tagged->ns == 1 && !tagged->d_gws, MCT_BAD_ARGUMENT, "a solved tagged-particle equation is needed");
+    MCT_REQUIRE(collective->Nk == tagged->Nk && collective->nt == tagged->nt && collective->opts.N == tagged->opts.N &&
+                    collective->opts.dt == tagged->opts.dt && collective->kernel->device == tagged->kernel->device,
+                MCT_BAD_ARGUMENT, "the two solutions must share the wavenumber grid, the time grid (tDict lookup) and the device");
+    const int ns = collective->kernel->Ns;
+    MCT_REQUIRE(s >= 0 && s < ns, MCT_BAD_ARGUMENT, "species index out of range (0-based)");
+    return msd_solve_common(tagged, collective->d_F, nullptr, collective->kernel->d_C, ns, s, full_species_sum ? ns : 1, rho_all, kBT,
+                            m_s, alpha, beta, gamma, delta, MSD0, dMSD0, t_out, msd_out, K_out, kernel_evals);
 }
 
 int mct_steady_state(mct_kernel_t h, const double *gamma, const double *F0, double tolerance, long max_iterations,

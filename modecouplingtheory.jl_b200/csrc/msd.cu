@@ -17,11 +17,27 @@ __global__ void msd_table_kernel(const MsdParams P) {
     __shared__ double red[kWarps];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     for (long it = blockIdx.x; it < P.nt; it += gridDim.x) {
-        const double *F = P.Fc + (size_t)it * P.Nk, *Fs = P.Fs + (size_t)it * P.Nk;
+        const double *Fs = P.Fs + (size_t)it * P.Nk;
         double s = 0.0;
-        for (int iq = threadIdx.x; iq < P.Nk; iq += blockDim.x) {
-            const double k = P.kvec[iq], c = P.Ck[iq];
-            s += k * k * k * k * (c * c) * F[iq] * Fs[iq];           // :581
+        if (!P.Cmix) {
+            const double *F = P.Fc + (size_t)it * P.Nk;
+            for (int iq = threadIdx.x; iq < P.Nk; iq += blockDim.x) {
+                const double k = P.kvec[iq], c = P.Ck[iq];
+                s += k * k * k * k * (c * c) * F[iq] * Fs[iq];       // :581
+            }
+        } else {
+            // MSDMultiComponentModeCouplingKernel3D (src/Kernels/MultiComponentKernels.jl:470-486):
+            //   K += k^4 C[a,s] C[s,b] F[a,b] Fs  for a, b = 1..Ns,  with  Ns = length(Fs[1])  (:477).
+            // Fs[1] is a Float64 there, so the reference's species sum only ever visits a = b = 1 and its golden
+            // (test/test_MCMCT.jl:226) is that number: species_terms = 1 reproduces it, species_terms = ns is the documented sum.
+            const int ns = P.ns, nb = ns * ns, sp = P.s;
+            const double *F = P.Fc + (size_t)it * P.Nk * nb;
+            for (int iq = threadIdx.x; iq < P.Nk; iq += blockDim.x) {
+                const double k = P.kvec[iq], k4 = k * k * k * k;
+                const double *Fb = F + (size_t)iq * nb, *Cb = P.Cmix + (size_t)iq * nb;
+                for (int a = 0; a < P.species_terms; a++)
+                    for (int b = 0; b < P.species_terms; b++) s += k4 * Cb[a + sp * ns] * Cb[sp + b * ns] * Fb[a + b * ns] * Fs[iq];
+            }
         }
         s = warp_sum(s);
         if (lane == 0) red[w] = s;
@@ -131,6 +147,19 @@ __global__ void msd_scalar_td_kernel(const MsdParams P) {
 #undef KINT
 }
 
+__global__ void mc_species_weight_kernel(const double *F, const double *C, int Nk, int ns, int s, long nt, double *G) {
+    const int nb = ns * ns;
+    const size_t n = (size_t)nt * Nk;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int q = (int)(i % Nk);
+        const double *Fb = F + i * nb, *Cb = C + (size_t)q * nb;     // column-major ns x ns blocks
+        double g = 0.0;
+        for (int a = 0; a < ns; a++)
+            for (int b = 0; b < ns; b++) g += Fb[a + b * ns] * Cb[s + a * ns] * Cb[s + b * ns];      // :352-357
+        G[i] = g;
+    }
+}
+
 __global__ void gather_slice_kernel(const double *src, int dof, const long *times, long n_times, const int *dofs, int n_dofs,
                                     double *dst) {
     const size_t n = (size_t)n_times * n_dofs;
@@ -148,6 +177,14 @@ int gather_slice_launch(const double *src, int dof, const long *d_times, long n_
     const size_t n = (size_t)n_times * n_dofs;
     const int blocks = (int)std::min<size_t>((n + kThreads - 1) / kThreads, 148 * 8);
     gather_slice_kernel<<<std::max(blocks, 1), kThreads, 0, stream>>>(src, dof, d_times, n_times, d_dofs, n_dofs, dst);
+    count_launch();
+    MCT_CUDA(cudaGetLastError());
+    return MCT_OK;
+}
+
+int mc_species_weight_launch(const double *F_traj, const double *Cblocks, int Nk, int ns, int s, long nt, double *G,
+                             cudaStream_t stream) {
+    mc_species_weight_kernel<<<148 * 8, kThreads, 0, stream>>>(F_traj, Cblocks, Nk, ns, s, nt, G);
     count_launch();
     MCT_CUDA(cudaGetLastError());
     return MCT_OK;

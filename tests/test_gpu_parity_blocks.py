@@ -130,3 +130,32 @@ def test_ddim_time_doubling_vs_oracle():
     ref = O.td_solve(O.ddim(p["rho"], 1.0, 1.0, p["k"], p["Sk"], 3), e["alpha"], e["beta"], e["gamma"], e["delta"], e["F0"], e["dF0"], **kw)
     assert np.max(np.abs(sol.F - ref["F"])) <= 1e-10
     assert abs(solver.kernel_evals - ref["kernel_evals"]) <= max(3, 0.01 * ref["kernel_evals"])
+
+
+def test_mc_tagged_and_msd_chain_goldens_test_MCMCT_212_226():
+    """Mixture -> tagged particle of species 2 -> its MSD, every step chained on the device-resident solution of the step
+    before (test/test_MCMCT.jl:196-226)."""
+    b = P.binary_mixture()
+    Nk = b["Nk"]
+    kw = dict(N=4, dt=1e-4, t_max=1e3, tolerance=1e-12, max_iterations=20000)
+    kern = pkg.MultiComponentModeCouplingKernel(b["rho"], 1.0, b["m"], b["k"], b["Sk"])
+    eq = pkg.MemoryEquation(1.0, 0.0, b["gamma"], np.zeros((Nk, 2, 2)), b["Sk"], np.zeros((Nk, 2, 2)), kern)
+    sol = pkg.solve(eq, pkg.TimeDoublingSolver(**kw))
+    s = 2                                                                                # the reference's 1-based species
+    tk = pkg.TaggedMultiComponentModeCouplingKernel(s, b["rho"], 1.0, b["m"], b["k"], b["Sk"], sol)
+    teq = pkg.MemoryEquation(1.0, 0.0, b["k"] ** 2 / b["m"][s - 1], 0.0, np.ones(Nk), np.zeros(Nk), tk)
+    tsol = pkg.solve(teq, pkg.TimeDoublingSolver(**kw))
+    assert tsol.F[-1][18] == pytest.approx(0.7678799482793754, rel=RTOL)                # test/test_MCMCT.jl:212
+    traj = sol.F.reshape(-1, Nk, 4)
+    otk = O.tagged_mc3d(s - 1, b["rho"], 1.0, b["m"], b["k"], b["Sk"], traj)
+    ots = O.td_solve(otk, 1.0, 0.0, b["k"] ** 2 / b["m"][s - 1], 0.0, np.ones(Nk), np.zeros(Nk), **kw)
+    # Newtonian dynamics amplify rounding differences of the kernel (the oracle sums per species pair, the device
+    # contracts the species weight first): same bar as the single-component Newtonian chain (test_gpu_parity.py)
+    assert np.max(np.abs(tsol.F - ots["F"])) < 5e-8
+    mk = pkg.MSDMultiComponentModeCouplingKernel(s, b["rho"], 1.0, b["m"], b["k"], b["Sk"], sol, tsol)
+    msol = pkg.solve(pkg.MemoryEquation(1.0, 0.0, 0.0, -6.0 / b["m"][s - 1], 0.0, 0.0, mk), pkg.TimeDoublingSolver(**kw))
+    assert msol.F.sum() == pytest.approx(0.6057207573375025, rel=RTOL)                  # test/test_MCMCT.jl:226
+    Kt = O.msd_mc3d_table(s - 1, b["rho"], 1.0, b["m"], b["k"], b["Sk"], traj, tsol.F)
+    assert np.allclose(msol.K, Kt, rtol=1e-11, atol=0)
+    oms = O.td_solve(O.tabulated(Kt), 1.0, 0.0, 0.0, -6.0 / b["m"][s - 1], [0.0], [0.0], scalar_mode=True, **kw)
+    assert np.max(np.abs(msol.F - np.ravel(oms["F"]))) <= 1e-9 * max(1.0, np.max(np.abs(oms["F"])))
