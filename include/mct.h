@@ -76,6 +76,10 @@ MCT_API int mct_mc3d_create(mct_kernel_t *out, int device, int Nk, int Ns, const
  * (src/Kernels/ModeCouplingKernels.jl:19-71). */
 MCT_API int mct_ddim_create(mct_kernel_t *out, int device, int Nk, const double *k_array, double prefactor, const double *V,
                     const double *J);
+/* ActiveMCTKernel from kernel.prefactor, kernel.J, kernel.V2 (Nk x Nk x Nk column-major [l,j,i], the OUTPUT index i last)
+ * (src/Kernels/ActiveMCTKernel.jl:1-49; evaluate_kernel! :51-61 is the dDim triple sum over another table). */
+MCT_API int mct_active_create(mct_kernel_t *out, int device, int Nk, const double *k_array, double prefactor, const double *J,
+                      const double *V2);
 /* evaluate_kernel!(out, kernel, F, t): F and out are dof doubles.  t_index is used by tagged kernels only. */
 MCT_API int mct_kernel_eval(mct_kernel_t kernel, const double *F, long t_index, double *out);
 /* n independent evaluations K_b = kernel(F_b), F and out are [n][dof] (parity tests, roofline measurement). */

@@ -659,6 +659,24 @@ int mct_ddim_create(mct_kernel_t *out, int device, int Nk, const double *k_array
     return MCT_OK;
 }
 
+int mct_active_create(mct_kernel_t *out, int device, int Nk, const double *k_array, double prefactor, const double *J, const double *V2) {
+    MCT_REQUIRE(V2 && J, MCT_BAD_ARGUMENT, "NULL argument to mct_active_create");
+    int rc = new_handle(out, K_DDIM, device, Nk, k_array);
+    if (rc) return rc;
+    mct_kernel_t h = *out;
+    const size_t n3 = (size_t)Nk * Nk * Nk;
+    double *tmp = nullptr;
+    cudaError_t e = cudaMalloc(&h->d_W, n3 * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&tmp, 2 * n3 * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(tmp, V2, n3 * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(tmp + n3, J, n3 * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) { rc = ddim_fuse_table(Nk, prefactor, tmp, tmp + n3, h->d_W, h->stream); if (rc) e = cudaErrorUnknown; }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(tmp);
+    if (e != cudaSuccess) { mct_kernel_destroy(h); *out = nullptr; return rc ? rc : cuda_fail(e, "mct_active_create", __FILE__, __LINE__); }
+    return MCT_OK;
+}
+
 int mct_kernel_destroy(mct_kernel_t h) {
     if (!h) return MCT_OK;
     cudaSetDevice(h->device);

@@ -784,10 +784,22 @@ __global__ void ddim_table_kernel(int Nk, const double *V, const double *J, doub
     }
 }
 
+// tables that already are [output][summed][summed] with the last index contiguous (ActiveMCTKernel, src/Kernels/ActiveMCTKernel.jl:28-49)
+__global__ void ddim_fuse_kernel(size_t n, const double *V, const double *J, double prefactor, double *W) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) W[i] = prefactor * J[i] * V[i];
+}
+
 }  // namespace
 
 int ddim_build_table(int Nk, double prefactor, const double *dV, const double *dJ, double *dW, cudaStream_t s) {
     ddim_table_kernel<<<1024, 256, 0, s>>>(Nk, dV, dJ, prefactor, dW);
+    count_launch();
+    MCT_CUDA(cudaGetLastError());
+    return MCT_OK;
+}
+
+int ddim_fuse_table(int Nk, double prefactor, const double *dV, const double *dJ, double *dW, cudaStream_t s) {
+    ddim_fuse_kernel<<<1024, 256, 0, s>>>((size_t)Nk * Nk * Nk, dV, dJ, prefactor, dW);
     count_launch();
     MCT_CUDA(cudaGetLastError());
     return MCT_OK;

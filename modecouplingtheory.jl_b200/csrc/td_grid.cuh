@@ -57,5 +57,7 @@ int td_grid_launch(const GridParams &P, int n_sm, cudaStream_t stream);
 
 // dDim: fused table W[iq][ik][ip] = prefactor * J[iq,ik,ip] * V[iq,ik,ip] from the reference's column-major arrays
 int ddim_build_table(int Nk, double prefactor, const double *dV, const double *dJ, double *dW, cudaStream_t s);
+// the same without the transposition, for tables stored [l, j, i] with the OUTPUT index last (ActiveMCTKernel)
+int ddim_fuse_table(int Nk, double prefactor, const double *dV, const double *dJ, double *dW, cudaStream_t s);
 
 }  // namespace mct

@@ -228,3 +228,35 @@ def steady_state(kernel, gamma, F0, tolerance=1e-8, max_iterations=10**6):
 def relaxation_time(t, F, threshold=np.exp(-1), mode="log"):
     t, tp = _d(t); F, Fp = _d(F)
     return lib().ok_relaxation_time(C.c_long(len(t)), tp, Fp, C.c_double(threshold), 0 if mode == "log" else 1)
+
+
+# ---- ActiveMCTKernel (src/Kernels/ActiveMCTKernel.jl:28-61): pure-Python restatement in the reference's loop order, for
+#      small Nk only (test infrastructure like everything in this file).
+def active_tables(rho, k, wk, w0, Sk, dim=3):
+    from math import gamma, pi
+    k = np.asarray(k, dtype=np.float64); wk = np.asarray(wk, dtype=np.float64); Sk = np.asarray(Sk, dtype=np.float64)
+    Nk = len(k)
+    dk = k[1] - k[0]
+    surf = 2 * pi ** ((dim - 1) / 2) / gamma((dim - 1) / 2)            # surface_d_dim_unit_sphere(dim-1), HelperFunctions.jl:258
+    prefactor = dk ** 2 * rho / (2 * (2 * pi) ** dim) * surf             # :30
+    mCk = 1 / rho * (1 - wk / (w0 * Sk))                               # :33
+    V2 = np.zeros((Nk, Nk, Nk)); J = np.zeros((Nk, Nk, Nk))           # indexed [l, j, i]
+    for i in range(1, Nk + 1):
+        for j in range(1, Nk + 1):
+            for l in range(abs(j - i) + 1, min(i + j - 1, Nk) + 1):   # :38
+                kk, q, p = k[i - 1], k[j - 1], k[l - 1]
+                cq, cp = mCk[j - 1], mCk[l - 1]
+                V = cq / (2 * kk) * (kk ** 2 + q ** 2 - p ** 2) + cp / (2 * kk) * (kk ** 2 + p ** 2 - q ** 2)   # :46
+                V2[l - 1, j - 1, i - 1] = wk[i - 1] * V ** 2
+                J[l - 1, j - 1, i - 1] = 2 * p * q / ((2 * kk) ** (dim - 2)) * ((q + p - kk) * (kk + p - q) * (kk + q - p) * (kk + p + q)) ** ((dim - 3) / 2)
+    return prefactor, J, V2
+
+
+def active_evaluate(prefactor, J, V2, F):
+    Nk = len(F)
+    out = np.zeros(Nk)
+    for i in range(1, Nk + 1):                                         # :56-58
+        for j in range(1, Nk + 1):
+            for l in range(abs(j - i) + 1, min(i + j - 1, Nk) + 1):
+                out[i - 1] += J[l - 1, j - 1, i - 1] * V2[l - 1, j - 1, i - 1] * F[j - 1] * F[l - 1]
+    return out * prefactor                                             # :59

@@ -159,3 +159,34 @@ def test_mc_tagged_and_msd_chain_goldens_test_MCMCT_212_226():
     assert np.allclose(msol.K, Kt, rtol=1e-11, atol=0)
     oms = O.td_solve(O.tabulated(Kt), 1.0, 0.0, 0.0, -6.0 / b["m"][s - 1], [0.0], [0.0], scalar_mode=True, **kw)
     assert np.max(np.abs(msol.F - np.ravel(oms["F"]))) <= 1e-9 * max(1.0, np.max(np.abs(oms["F"])))
+
+
+def test_active_mct_kernel_eval_solve_and_steady_state_test_ActiveMCT():
+    """ActiveMCTKernel is the dDim triple sum over another table (output index last).  Kernel evaluation
+    against the oracle's loop restatement; the reference's own checks (test/test_ActiveMCT.jl:16-32): with w(k)=w0=1 the
+    solve and the steady state equal the passive 3D kernel's (rtol 1e-5), and w0 = 0.8 changes the result."""
+    Nk = 20
+    p = P.hard_spheres(Nk, 0.51 * np.pi / 6, kmax=20.0)
+    rho, k, Sk = 0.51, p["k"], p["Sk"]
+    rng = np.random.default_rng(0)
+    for dim, wk, w0 in ((3, np.ones(Nk), 1.0), (3, np.linspace(0.8, 1.2, Nk), 0.9), (2, np.linspace(0.8, 1.2, Nk), 0.9)):
+        ka = pkg.ActiveMCTKernel(rho, k, wk, w0, Sk, dim)
+        pref, J, V2 = O.active_tables(rho, k, wk, w0, Sk, dim)
+        F = rng.random(Nk)
+        assert np.allclose(pkg.evaluate_kernel(ka, F), O.active_evaluate(pref, J, V2, F), rtol=1e-12, atol=0)
+    wk = np.ones(Nk)
+    gamma = k ** 2 * wk / Sk
+    kw = dict(N=8, dt=1e-6, t_max=1e4, tolerance=1e-10)
+    passive = pkg.solve(pkg.MemoryEquation(1.0, 0.0, gamma, 0.0, Sk, np.zeros(Nk), pkg.ModeCouplingKernel(rho, 1.0, 1.0, k, Sk)),
+                        pkg.TimeDoublingSolver(**kw))
+    ka = pkg.ActiveMCTKernel(rho, k, wk, 1.0, Sk, 3)
+    active = pkg.solve(pkg.MemoryEquation(1.0, 0.0, gamma, 0.0, Sk, np.zeros(Nk), ka), pkg.TimeDoublingSolver(**kw))
+    assert active.F.sum() == pytest.approx(passive.F.sum(), rel=1e-5)                   # test/test_ActiveMCT.jl:22
+    assert pkg.find_relaxation_time(active.t, active.F[:, 5]) == pytest.approx(
+        pkg.find_relaxation_time(passive.t, passive.F[:, 5]), rel=1e-5)                  # :23
+    ss_p = pkg.solve_steady_state(gamma, Sk, pkg.ModeCouplingKernel(rho, 1.0, 1.0, k, Sk))
+    ss_a = pkg.solve_steady_state(gamma, Sk, ka)
+    assert ss_a.F.sum() == pytest.approx(ss_p.F.sum(), rel=1e-5)                        # :24
+    kb = pkg.ActiveMCTKernel(rho, k, wk, 0.8, Sk, 3)
+    other = pkg.solve(pkg.MemoryEquation(1.0, 0.0, gamma, 0.0, Sk, np.zeros(Nk), kb), pkg.TimeDoublingSolver(**kw))
+    assert abs(other.F.sum() - active.F.sum()) > 1e-3 * abs(active.F.sum())              # :32

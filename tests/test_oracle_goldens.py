@@ -142,3 +142,23 @@ def test_relaxation_time_test_relaxationtime_6_8():
     F = np.exp(-t / 1e5) * 6
     assert abs(O.relaxation_time(t, F, mode="log") - 1e5) < 0.1
     assert abs(O.relaxation_time(t, F, mode="lin") - 1e5) < 1.0
+
+
+def test_active_kernel_equals_passive_kernel_test_ActiveMCT_16_22():
+    """ActiveMCTKernel with w(k) = w0 = 1 is the passive 3D kernel (test/test_ActiveMCT.jl:1-24 checks that through the
+    solves); here: the oracle's loop restatement against the Bengtzelius oracle, and the host table builder of the
+    product against the loops."""
+    p = P.hard_spheres(20, 0.51 * np.pi / 6, kmax=20.0)
+    rho = 0.51
+    pref, J, V2 = O.active_tables(rho, p["k"], np.ones(20), 1.0, p["Sk"], 3)
+    F = p["Sk"] * np.exp(-0.1 * p["k"])
+    Ka = O.active_evaluate(pref, J, V2, F)
+    Kp = O.sc3d(rho, 1.0, 1.0, p["k"], p["Sk"]).evaluate(F)
+    assert np.abs(Ka - Kp).sum() < 1e-8 * np.abs(Kp).sum()
+    from conftest import load_pkg
+    pkg = load_pkg()
+    for dim in (3, 2):
+        a = pkg.active_tables(rho, p["k"], np.linspace(0.8, 1.2, 20), 0.9, p["Sk"], dim)
+        b = O.active_tables(rho, p["k"], np.linspace(0.8, 1.2, 20), 0.9, p["Sk"], dim)
+        assert a[0] == pytest.approx(b[0], rel=1e-15)
+        assert np.allclose(a[1], b[1], rtol=1e-13, atol=0) and np.allclose(a[2], b[2], rtol=1e-13, atol=0)
