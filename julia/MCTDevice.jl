@@ -87,3 +87,52 @@ function solve(eq::MemoryEquation, s::DeviceTimeDoublingSolver)
     # same container types as the reference: Vector of per-time vectors / Diagonals (Solvers.jl:19-24)
     MemoryEquationSolution(t, [F[:, i] for i in 1:nt[]], [Diagonal(K[:, i]) for i in 1:nt[]], s)
 end
+
+# ---- the steps after the collective solve, chained on device-resident solutions (include/mct.h) -------------------
+# A maintainer would keep the equation handle `q` (mct_equation_create / _solve / _download instead of mct_td_solve) in a
+# `DeviceSolution <: Any` next to the MemoryEquationSolution and add these methods; nothing but handles and nt-sized
+# vectors crosses PCIe.  Species / wavenumber / time indices are 0-based on the C side.
+
+# get_F(sol, its, iks)  (src/HelperFunctions.jl:169-210)
+function device_slice(q::Ptr{Cvoid}, its::Vector{Int}, iks::Vector{Int})
+    t = Vector{Float64}(undef, length(its)); F = Matrix{Float64}(undef, length(iks), length(its)); K = similar(F)
+    mct_check(ccall((:mct_equation_download_slice, libmct), Cint,
+        (Ptr{Cvoid}, Clong, Ptr{Clong}, Cint, Ptr{Cint}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
+        q, length(its), Clong.(its .- 1), length(iks), Cint.(iks .- 1), t, F, K))
+    t, F, K
+end
+
+# find_relaxation_time(get_t(sol), get_F(sol, :, ik); threshold, mode)  (src/RelaxationTime.jl:14-39)
+function device_relaxation_times(q::Ptr{Cvoid}, iks::Vector{Int}; threshold=exp(-1), mode=:log)
+    τ = Vector{Float64}(undef, length(iks))
+    mct_check(ccall((:mct_equation_relaxation_times, libmct), Cint, (Ptr{Cvoid}, Cint, Ptr{Cint}, Cdouble, Cint, Ptr{Cdouble}),
+        q, length(iks), Cint.(iks .- 1), threshold, mode == :log ? 0 : 1, τ))
+    τ
+end
+
+# TaggedMultiComponentModeCouplingKernel(s, ρ, kBT, m, k_array, Sₖ, sol)  (src/Kernels/MultiComponentKernels.jl:268-333)
+function device_tagged_mc_kernel(s::Int, ρ, kBT, m, q_mixture::Ptr{Cvoid})
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    mct_check(ccall((:mct_mc3d_tagged_create_from_equation, libmct), Cint, (Ref{Ptr{Cvoid}}, Cint, Cdouble, Cdouble, Cdouble, Ptr{Cvoid}),
+        h, s - 1, sum(ρ), kBT, m[s], q_mixture))
+    h[]
+end
+
+# solve(MemoryEquation(α, β, γ, δ, msd0, dmsd0, MSDModeCouplingKernel(ρ, kBT, m, k_array, Sₖ, sol, taggedsol)), solver)
+# (src/Kernels/ModeCouplingKernels.jl:552-586 + the scalar branch of src/TimeDoublingSolver.jl)
+function device_msd(q::Ptr{Cvoid}, q_tagged::Ptr{Cvoid}, ρ, kBT, m, Sₖ::Vector{Float64}, α, β, γ, δ, msd0, dmsd0, nt::Int)
+    t = Vector{Float64}(undef, nt); msd = similar(t); K = similar(t); evals = Ref{Clong}(0)
+    mct_check(ccall((:mct_msd3d_solve, libmct), Cint,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Cdouble, Cdouble, Ptr{Cdouble}, Cdouble, Cdouble, Cdouble, Cdouble, Cdouble, Cdouble,
+         Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ref{Clong}),
+        q, q_tagged, ρ, kBT, m, Sₖ, α, β, γ, δ, msd0, dmsd0, t, msd, K, evals))
+    t, msd, K, evals[]
+end
+
+# ActiveMCTKernel(ρ, k_array, wk, w0, Sk, dim)  (src/Kernels/ActiveMCTKernel.jl:28-49): J and V2 are [l, j, i], the device layout
+function device_kernel(k::ActiveMCTKernel, dev::Integer)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    mct_check(ccall((:mct_active_create, libmct), Cint, (Ref{Ptr{Cvoid}}, Cint, Cint, Ptr{Cdouble}, Cdouble, Ptr{Cdouble}, Ptr{Cdouble}),
+        h, dev, length(k.k_array), k.k_array, k.prefactor, k.J, k.V2))
+    h[]
+end
