@@ -3,7 +3,10 @@
 #include <atomic>
 #include <cmath>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
+#include <functional>
+#include <unistd.h>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -57,6 +60,9 @@ struct mct_kernel_s {
     double *d_scratch = nullptr; size_t scratch_doubles = 0;
     double *d_io = nullptr; size_t io_doubles = 0;
     int n_sm = 0; size_t smem_optin = 0;
+    // retired device buffers kept for the next request of exactly the same size (mct_td_solve in a loop: cudaMalloc and
+    // above all cudaFree cost 5 ms to several 100 ms per solve otherwise -- both synchronise with the driver)
+    std::vector<std::pair<void *, size_t>> pool;
 };
 
 struct mct_equation_s {
@@ -66,6 +72,7 @@ struct mct_equation_s {
     mct_td_options opts{};
     double *d_coef = nullptr;   // alpha, beta, gamma, delta, F0, dF0  [6][Nk]
     double *d_ring = nullptr, *d_F = nullptr, *d_K = nullptr;
+    size_t coef_bytes = 0, ring_bytes = 0, traj_bytes = 0;   // set when the buffers come from the kernel's pool
     int *d_status = nullptr;
     long long *d_evals = nullptr;
     bool solved = false;
@@ -79,6 +86,18 @@ struct mct_equation_s {
 };
 
 namespace mct {
+
+static constexpr size_t kPoolEntries = 8;
+static cudaError_t pool_alloc(mct_kernel_t h, void **p, size_t bytes) {
+    for (size_t i = 0; i < h->pool.size(); i++)
+        if (h->pool[i].second == bytes) { *p = h->pool[i].first; h->pool.erase(h->pool.begin() + i); return cudaSuccess; }
+    return cudaMalloc(p, bytes);
+}
+static void pool_free(mct_kernel_t h, void *p, size_t bytes) {
+    if (!p) return;
+    if (h && h->pool.size() < kPoolEntries) h->pool.emplace_back(p, bytes);
+    else cudaFree(p);
+}
 
 static int ensure_scratch(mct_kernel_t h, size_t doubles) {
     if (h->scratch_doubles >= doubles) return MCT_OK;
@@ -286,6 +305,9 @@ static int expand_coef(int kind, double lam, const double *arr, int Nk, double *
 }
 
 // One persistent launch for a batch of equations that share kernel geometry and solver options.
+// Set by mct_td_solve around the solve: called once with the event that marks the end of the launch, while the kernel runs.
+static thread_local std::function<void(cudaEvent_t)> *g_overlap = nullptr;
+
 static int run_batch(int n, mct_equation_t *eqs, int mode, double tol, long long max_iter, int *status, long long *evals,
                      float *device_ms) {
     MCT_REQUIRE(n >= 1 && eqs != nullptr, MCT_BAD_ARGUMENT, "empty batch");
@@ -360,7 +382,7 @@ static int run_batch(int n, mct_equation_t *eqs, int mode, double tol, long long
     unsigned char *comm = nullptr;
     const size_t pbytes = (size_t)P.G * kProfSlots * sizeof(long long);
     const size_t total = xbytes + qbytes + 256 + ebytes + pbytes;
-    MCT_CUDA(cudaMalloc(&comm, total));
+    MCT_CUDA(pool_alloc(h0, (void **)&comm, total));
     cudaError_t ce = cudaMemsetAsync(comm, 0, total, s);
     if (ce == cudaSuccess) ce = cudaMemsetAsync(comm, 0xFF, xbytes + qbytes, s);
     for (int t = 0; t < nteams && ce == cudaSuccess; t++)      // arrival counters start at zero
@@ -381,6 +403,7 @@ static int run_batch(int n, mct_equation_t *eqs, int mode, double tol, long long
         rc = td_sc_launch(P, s);
         if (rc == MCT_OK) {
             ce = cudaEventRecord(ev1, s);
+            if (ce == cudaSuccess && g_overlap) (*g_overlap)(ev1);          // host work while the persistent kernel runs
             if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
             float ms = 0.f;
             if (ce == cudaSuccess) ce = cudaEventElapsedTime(&ms, ev0, ev1);
@@ -390,7 +413,7 @@ static int run_batch(int n, mct_equation_t *eqs, int mode, double tol, long long
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     if (ce != cudaSuccess) { cudaFree(comm); return cuda_fail(ce, "run_batch", __FILE__, __LINE__); }
-    if (rc != MCT_OK) { cudaFree(comm); return rc; }
+    if (rc != MCT_OK) { pool_free(h0, comm, total); return rc; }
 #ifdef MCT_PROFILE
     {
         std::vector<long long> pr((size_t)P.G * kProfSlots);
@@ -430,7 +453,7 @@ static int run_batch(int n, mct_equation_t *eqs, int mode, double tol, long long
         eqs[i]->solved = (st == MCT_OK);
         if (st != MCT_OK && worst == MCT_OK) worst = st;
     }
-    cudaFree(comm);
+    pool_free(h0, comm, total);
     if (worst == MCT_NOT_CONVERGED)
         set_error("Iteration did not converge. Either increase the number of time steps before a time doubling, or choose a "
                   "different memory kernel.");
@@ -685,6 +708,7 @@ int mct_kernel_destroy(mct_kernel_t h) {
     if (h->owns_Fc) cudaFree(h->d_Fc);
     for (auto &kv : h->slabs) cudaFree(kv.second);
     cudaFree(h->d_scratch); cudaFree(h->d_io);
+    for (auto &pe : h->pool) cudaFree(pe.first);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return MCT_OK;
@@ -819,10 +843,11 @@ int mct_equation_create(mct_equation_t *out, mct_kernel_t h, const mct_coeffs *c
             if (host[Nk + i] == 0.0) { delete q; set_error("alpha = 0 needs beta != 0"); return MCT_BAD_ARGUMENT; }
     }
     const size_t ring = (size_t)4 * Nk * 4 * o->N, traj = (size_t)q->nt * Nk;
-    cudaError_t e = cudaMalloc(&q->d_coef, host.size() * sizeof(double));
-    if (e == cudaSuccess) e = cudaMalloc(&q->d_ring, ring * sizeof(double));
-    if (e == cudaSuccess) e = cudaMalloc(&q->d_F, 2 * traj * sizeof(double));
-    if (e == cudaSuccess) e = cudaMalloc(&q->d_status, 64);
+    q->coef_bytes = host.size() * sizeof(double); q->ring_bytes = ring * sizeof(double); q->traj_bytes = 2 * traj * sizeof(double);
+    cudaError_t e = pool_alloc(h, (void **)&q->d_coef, q->coef_bytes);
+    if (e == cudaSuccess) e = pool_alloc(h, (void **)&q->d_ring, q->ring_bytes);
+    if (e == cudaSuccess) e = pool_alloc(h, (void **)&q->d_F, q->traj_bytes);
+    if (e == cudaSuccess) e = pool_alloc(h, (void **)&q->d_status, 64);
     if (e == cudaSuccess) {
         q->d_K = q->d_F + traj;
         q->d_evals = (long long *)((char *)q->d_status + 16);
@@ -841,7 +866,12 @@ int mct_equation_destroy(mct_equation_t q) {
     if (q->d_gws) { cudaFree(q->d_gws); q->d_F = nullptr; }
     for (int r = 0; r < kMaxShardRanks; r++) if (q->peer_maps[r]) cudaIpcCloseMemHandle(q->peer_maps[r]);
     cudaFree(q->d_xshard);
-    cudaFree(q->d_coef); cudaFree(q->d_ring); cudaFree(q->d_F); cudaFree(q->d_status);
+    if (q->traj_bytes && q->kernel) {                  // single-component equation: buffers go back to the kernel's pool
+        pool_free(q->kernel, q->d_coef, q->coef_bytes); pool_free(q->kernel, q->d_ring, q->ring_bytes);
+        pool_free(q->kernel, q->d_F, q->traj_bytes); pool_free(q->kernel, q->d_status, 64);
+    } else {
+        cudaFree(q->d_coef); cudaFree(q->d_ring); cudaFree(q->d_F); cudaFree(q->d_status);
+    }
     delete q;
     return MCT_OK;
 }
@@ -984,14 +1014,92 @@ int mct_equation_relaxation_times(mct_equation_t q, int n_k, const int *ik, doub
     return MCT_OK;
 }
 
+// Download of the trajectory WHILE the persistent kernel produces it (single-component solves through mct_td_solve).
+// The trajectory is pre-filled with a NaN payload no arithmetic produces; every output word is written exactly once, so a
+// word that is not the sentinel is final -- no ordering between the kernel's stores is assumed.  Per time block (2N
+// rows) the host polls the block's last row (8 Nk bytes), then copies the block on a second stream and accepts it when no
+// sentinel is left in it.  70 MB hide behind a 330 ms solve even on a slow PCIe link; whatever is still missing when
+// the kernel ends (or after an aborted solve) is copied by the plain download afterwards.
+static long stream_download(mct_equation_t q, double *F_out, double *K_out, cudaEvent_t done) {
+    const int Nk = q->Nk, n2 = 2 * q->opts.N;
+    const unsigned long long sentinel = 0xFFFFFFFFFFFFFFFFull;
+    cudaStream_t sb = nullptr;
+    if (cudaStreamCreateWithFlags(&sb, cudaStreamNonBlocking) != cudaSuccess) return 0;
+    auto clean = [&](const double *p, size_t n) {
+        const unsigned long long *u = (const unsigned long long *)p;
+        for (size_t i = 0; i < n; i++) if (u[i] == sentinel) return false;
+        return true;
+    };
+    long row = 0;                                       // rows [0, row) are on the host
+    bool alive = true;
+    while (alive && row < q->nt) {
+        const long rows = (row == 0) ? 1 + n2 : n2;     // t = 0 and the bootstrap first, then one time block at a time
+        const size_t off = (size_t)row * Nk, n = (size_t)rows * Nk, last = off + n - Nk;
+        bool got = false;
+        while (!got) {
+            const bool finished = cudaEventQuery(done) == cudaSuccess;
+            if (cudaMemcpyAsync(F_out + last, q->d_F + last, Nk * sizeof(double), cudaMemcpyDeviceToHost, sb) != cudaSuccess ||
+                cudaMemcpyAsync(K_out + last, q->d_K + last, Nk * sizeof(double), cudaMemcpyDeviceToHost, sb) != cudaSuccess ||
+                cudaStreamSynchronize(sb) != cudaSuccess) { alive = false; break; }
+            if (clean(F_out + last, Nk) && clean(K_out + last, Nk)) {
+                if (cudaMemcpyAsync(F_out + off, q->d_F + off, n * sizeof(double), cudaMemcpyDeviceToHost, sb) != cudaSuccess ||
+                    cudaMemcpyAsync(K_out + off, q->d_K + off, n * sizeof(double), cudaMemcpyDeviceToHost, sb) != cudaSuccess ||
+                    cudaStreamSynchronize(sb) != cudaSuccess) { alive = false; break; }
+                got = clean(F_out + off, n) && clean(K_out + off, n);
+            }
+            if (!got) {
+                if (finished) { alive = false; break; }   // the kernel is done and the block is not there: failed solve
+                usleep(300);
+            }
+        }
+        if (got) row += rows;
+    }
+    cudaStreamDestroy(sb);
+    return row;
+}
+
 int mct_td_solve(mct_kernel_t h, const mct_coeffs *c, const double *F0, const double *dF0, const mct_td_options *o,
                  double *t_out, double *F_out, double *K_out, long *kernel_evals) {
     mct_equation_t q = nullptr;
+    const auto w0 = std::chrono::steady_clock::now();
     int rc = mct_equation_create(&q, h, c, F0, dF0, o);
     if (rc) return rc;
-    rc = mct_equation_solve(q, kernel_evals, nullptr);
-    int rc2 = mct_equation_download(q, t_out, F_out, K_out);
+    const auto w1 = std::chrono::steady_clock::now();
+    float dev_ms = 0.f;
+    long have = 0;
+    const bool streamed = !is_grid_kernel(h) && F_out && K_out && env_int("MCT_STREAM_DOWNLOAD", 1);
+    if (streamed) {
+        const size_t traj = (size_t)q->nt * q->Nk;
+        cudaError_t e = cudaMemsetAsync(q->d_F, 0xFF, traj * sizeof(double), h->stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(q->d_K, 0xFF, traj * sizeof(double), h->stream);
+        if (e != cudaSuccess) { mct_equation_destroy(q); return cuda_fail(e, "mct_td_solve", __FILE__, __LINE__); }
+        std::function<void(cudaEvent_t)> overlap = [&](cudaEvent_t done) { have = stream_download(q, F_out, K_out, done); };
+        g_overlap = &overlap;
+        rc = mct_equation_solve(q, kernel_evals, &dev_ms);
+        g_overlap = nullptr;
+    } else {
+        rc = mct_equation_solve(q, kernel_evals, &dev_ms);
+    }
+    const auto w2 = std::chrono::steady_clock::now();
+    const long streamed_rows = have;
+    int rc2 = MCT_OK;
+    if (have < q->nt) {                                  // the rest (everything, when nothing was streamed)
+        const size_t off = (size_t)have * q->Nk * q->ns * q->ns, n = (size_t)(q->nt - have) * q->Nk * q->ns * q->ns;
+        cudaError_t e = cudaSuccess;
+        if (F_out) e = cudaMemcpy(F_out + off, q->d_F + off, n * sizeof(double), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && K_out) e = cudaMemcpy(K_out + off, q->d_K + off, n * sizeof(double), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc2 = cuda_fail(e, "mct_td_solve download", __FILE__, __LINE__);
+    }
+    if (rc2 == MCT_OK && t_out) rc2 = mct_equation_download(q, t_out, nullptr, nullptr);
+    const auto w3 = std::chrono::steady_clock::now();
+    const long nt_all = q->nt;
     mct_equation_destroy(q);
+    if (env_int("MCT_VERBOSE", 0)) {
+        const auto w4 = std::chrono::steady_clock::now();
+        auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+        fprintf(stderr, "[mct] mct_td_solve: create %.2f ms, solve %.2f ms (kernel %.2f ms, %ld of %ld rows streamed), rest of download %.2f ms, destroy %.2f ms\n",
+                ms(w0, w1), ms(w1, w2), dev_ms, streamed_rows, nt_all, ms(w2, w3), ms(w3, w4));
+    }
     return rc ? rc : rc2;
 }
 

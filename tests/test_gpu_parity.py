@@ -297,3 +297,26 @@ def test_slice_download_and_relaxation_times_match_the_full_trajectory():
                                          download=dict(times=[0, nt - 1], dofs=[18], K=False))
     assert status == [0] and sols[0].F.shape == (2, 1)
     assert np.allclose(sols[0].F[:, 0], sol.F[[0, nt - 1], 18], rtol=0, atol=1e-10)
+
+
+@pytest.mark.parametrize("Nk,eta", [(100, 0.51), (1000, 0.50)])
+def test_streamed_download_of_mct_td_solve_equals_the_resident_solution(Nk, eta):
+    """mct_td_solve copies the trajectory to the host buffers WHILE the persistent kernel produces it (sentinel-validated
+    time blocks); the result must be bit-identical to solving resident and downloading afterwards."""
+    p = P.hard_spheres(Nk, eta)
+    e = P.overdamped(p)
+    kw = dict(N=16, dt=1e-8, t_max=1e4, tolerance=1e-10)
+    kern = gpu_kernel(p)
+    eq = pkg.MemoryEquation(e["alpha"], e["beta"], e["gamma"], e["delta"], e["F0"], e["dF0"], kern)
+    ref = pkg.solve(eq, pkg.TimeDoublingSolver(**kw))
+    nt = ref.F.shape[0]
+    for _ in range(3):
+        t = np.full(nt, np.nan); F = np.full((nt, Nk), np.nan); K = np.full((nt, Nk), np.nan)
+        s2 = pkg.TimeDoublingSolver(**kw)
+        pkg.api.solve_into(eq, s2, t, F, K)
+        assert np.array_equal(t, ref.t) and np.array_equal(F, ref.F) and np.array_equal(K, ref.K)
+        assert s2.kernel_evals == ref.solver.kernel_evals
+    # a solve that does not converge must return its error, not wait for blocks that never come
+    t = np.empty(nt); F = np.empty((nt, Nk)); K = np.empty((nt, Nk))
+    with pytest.raises(pkg.DomainError):
+        pkg.api.solve_into(eq, pkg.TimeDoublingSolver(max_iterations=1, **kw), t, F, K)
