@@ -80,6 +80,10 @@ MCT_API int mct_ddim_create(mct_kernel_t *out, int device, int Nk, const double 
  * (src/Kernels/ActiveMCTKernel.jl:1-49; evaluate_kernel! :51-61 is the dDim triple sum over another table). */
 MCT_API int mct_active_create(mct_kernel_t *out, int device, int Nk, const double *k_array, double prefactor, const double *J,
                       const double *V2);
+/* TaggedActiveMCTKernel (src/Kernels/ActiveMCTKernel.jl:63-136) chained on the device-resident collective solution:
+ * out[i] = prefactor sum_{j,l} J[l,j,i] V2[l,j,i] F_collective(t)[l] Fs[j]  (:125-136), tDict lookup = output index. */
+MCT_API int mct_active_tagged_create_from_equation(mct_kernel_t *out, int Nk, const double *k_array, double prefactor, const double *J,
+                                           const double *V2, mct_equation_t collective);
 /* evaluate_kernel!(out, kernel, F, t): F and out are dof doubles.  t_index is used by tagged kernels only. */
 MCT_API int mct_kernel_eval(mct_kernel_t kernel, const double *F, long t_index, double *out);
 /* n independent evaluations K_b = kernel(F_b), F and out are [n][dof] (parity tests, roofline measurement). */

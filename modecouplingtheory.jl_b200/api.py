@@ -54,7 +54,7 @@ EXPORTS = [
     "mct_ddim_create", "mct_kernel_eval", "mct_kernel_eval_many", "mct_kernel_destroy", "mct_td_output_len", "mct_td_solve",
     "mct_equation_create", "mct_equation_solve", "mct_equation_download", "mct_equation_destroy", "mct_equation_solve_batch", "mct_equation_shard_prepare", "mct_equation_shard_connect",
     "mct_steady_state", "mct_msd3d_solve", "mct_equation_download_slice", "mct_equation_relaxation_times",
-    "mct_mc3d_tagged_create_from_equation", "mct_msd_mc3d_solve", "mct_active_create",
+    "mct_mc3d_tagged_create_from_equation", "mct_msd_mc3d_solve", "mct_active_create", "mct_active_tagged_create_from_equation",
 ]
 
 
@@ -396,6 +396,36 @@ def ActiveMCTKernel(rho, k_array, wk, w0, Sk, dim=3, device=0):
     h = C.c_void_p()
     _check(L.mct_active_create(C.byref(h), device, len(k), _p(k), C.c_double(prefactor), _p(J), _p(V2)))
     return MemoryKernel(h, len(k), 1, device)
+
+
+def tagged_active_tables(rho, k_array, wk, w0, Sk, dim=3):
+    """prefactor, J[l, j, i], V2[l, j, i] of TaggedActiveMCTKernel -- src/Kernels/ActiveMCTKernel.jl:96-117."""
+    k = _arr(k_array); Sk = _arr(Sk); wk = _arr(wk)
+    Nk = len(k)
+    dk = k[1] - k[0]
+    prefactor = rho * dk ** 2 / ((2 * np.pi) ** dim) * _surface_d_dim_unit_sphere(dim - 1)
+    mCk = 1 / rho * (1 - wk / (w0 * Sk))
+    il, ij, ii = np.meshgrid(np.arange(1, Nk + 1), np.arange(1, Nk + 1), np.arange(1, Nk + 1), indexing="ij")
+    kk, q, p = k[ii - 1], k[ij - 1], k[il - 1]
+    inside = (np.abs(ij - ii) + 1 <= il) & (il <= np.minimum(ii + ij - 1, Nk))
+    V2 = np.where(inside, (mCk[il - 1] / (2 * kk) * (kk ** 2 + p ** 2 - q ** 2)) ** 2 * w0, 0.0)
+    base = np.where(inside, (q + p - kk) * (kk + p - q) * (kk + q - p) * (kk + p + q), 1.0)
+    J = np.where(inside, 2 * p * q / ((2 * kk) ** (dim - 2)) * base ** ((dim - 3) / 2), 0.0)
+    return prefactor, np.asfortranarray(J), np.asfortranarray(V2)
+
+
+def TaggedActiveMCTKernel(rho, k_array, wk, w0, Sk, Fsol, dim=3):
+    """TaggedActiveMCTKernel(ρ, k_array, wk, w0, Sk, Fsol, dim) -- src/Kernels/ActiveMCTKernel.jl:96-117; `Fsol` is the
+    device-resident collective solution (the tDict lookup becomes the output index)."""
+    if getattr(Fsol, "_equation", None) is None:
+        raise MCTDeviceError("TaggedActiveMCTKernel needs the device-resident collective solution")
+    L = load_library()
+    k = _arr(k_array)
+    prefactor, J, V2 = tagged_active_tables(rho, k, wk, w0, Sk, dim)
+    h = C.c_void_p()
+    _check(L.mct_active_tagged_create_from_equation(C.byref(h), len(k), _p(k), C.c_double(prefactor), _p(J), _p(V2),
+                                                    Fsol._equation._q))
+    return MemoryKernel(h, len(k), 1, Fsol._equation._kernel.device, keep=(Fsol._equation,))
 
 
 def evaluate_kernel(kernel, F, t=0):

@@ -496,6 +496,7 @@ static int grid_setup(mct_equation_t q, mct_kernel_t h, int mode, const std::vec
     g.type = (h->type == K_MC3D) ? GK_MC3D : GK_DDIM; g.Nk = Nk; g.ns = ns; g.mode = mode;
     g.rank = 0; g.world = 1; g.spin_limit_cycles = (long long)env_int("MCT_SHARD_SPIN_LIMIT_MS", 20000) * 2000000LL;
     g.kvec = h->d_k; g.C = h->d_C; g.pref = h->d_pref; g.W = h->d_W;
+    g.Fc = (h->type == K_DDIM) ? h->d_Fc : nullptr; g.nt_c = h->nt; g.tix0 = 0;
     double *p = q->d_gws;
     g.alpha = p; g.beta = p + dof; g.gamma = p + 2 * dof; g.delta = p + 3 * dof; g.F0 = p + 4 * dof; g.dF0 = p + 5 * dof; p += 6 * dof;
     g.Ft = p; g.Kt = p + ring; g.FI = p + 2 * ring; g.KI = p + 3 * ring; p += 4 * ring;
@@ -700,6 +701,16 @@ int mct_active_create(mct_kernel_t *out, int device, int Nk, const double *k_arr
     return MCT_OK;
 }
 
+int mct_active_tagged_create_from_equation(mct_kernel_t *out, int Nk, const double *k_array, double prefactor, const double *J,
+                                           const double *V2, mct_equation_t collective) {
+    MCT_REQUIRE(collective && collective->solved && collective->mode == 0 && collective->ns == 1 && collective->Nk == Nk,
+                MCT_BAD_ARGUMENT, "a solved scalar-valued collective equation with the same Nk is needed");
+    int rc = mct_active_create(out, collective->kernel->device, Nk, k_array, prefactor, J, V2);
+    if (rc) return rc;
+    (*out)->nt = collective->nt; (*out)->d_Fc = collective->d_F; (*out)->owns_Fc = false;
+    return MCT_OK;
+}
+
 int mct_kernel_destroy(mct_kernel_t h) {
     if (!h) return MCT_OK;
     cudaSetDevice(h->device);
@@ -752,7 +763,8 @@ int mct_kernel_eval(mct_kernel_t h, const double *F, long t_index, double *out) 
         int rc = grid_setup(&q, h, 2, host);
         double *dF = nullptr;
         if (!rc) { cudaError_t e = cudaMalloc(&dF, dof * sizeof(double)); if (e == cudaSuccess) e = cudaMemcpy(dF, F, dof * sizeof(double), cudaMemcpyHostToDevice); if (e != cudaSuccess) rc = cuda_fail(e, "mct_kernel_eval", __FILE__, __LINE__); }
-        if (!rc) { q.gp.Fin = dF; rc = grid_run(&q, nullptr, nullptr, nullptr); }
+        if (!rc && q.gp.Fc && (t_index < 0 || t_index >= h->nt)) { set_error("t is not a time of the collective solution (tDict KeyError)"); rc = MCT_BAD_ARGUMENT; }
+        if (!rc) { q.gp.Fin = dF; q.gp.tix0 = t_index; rc = grid_run(&q, nullptr, nullptr, nullptr); }
         if (!rc) { cudaError_t e = cudaMemcpy(out, q.gp.F_out, dof * sizeof(double), cudaMemcpyDeviceToHost); if (e != cudaSuccess) rc = cuda_fail(e, "mct_kernel_eval", __FILE__, __LINE__); }
         cudaFree(dF); cudaFree(q.d_gws);
         return rc;

@@ -131,6 +131,7 @@ struct Ctx {
     int dof, gtid, gthreads, lane, gwarp, gwarps;
     int ge, ga, gb, gbase; bool gact;
     unsigned xepoch = 0;
+    long tix = 0;                 // time index of the evaluation in progress (tagged dense kernels)
     bool failed = false;
     long long tp;
     __device__ Ctx(const GridParams &p) : P(p), grid(cg::this_grid()) {
@@ -498,12 +499,14 @@ struct Ctx {
     __device__ void eval_ddim(const double *F, double *Kout) {
         const int Nk = P.Nk;
         __shared__ double red[kGT / 32];
+        // tagged variant (src/Kernels/ActiveMCTKernel.jl:125-136): the second factor is the collective F at this time
+        const double *F2 = P.Fc ? P.Fc + (size_t)tix * Nk : F;
         for (int iq = blockIdx.x; iq < Nk; iq += gridDim.x) {
             const double *W = P.W + (size_t)iq * Nk * Nk;
             double s = 0.0;
             for (int i = threadIdx.x; i < Nk * Nk; i += blockDim.x) {
                 const int ik = i / Nk, ip = i - ik * Nk;
-                s += W[i] * F[ik] * F[ip];
+                s += W[i] * F[ik] * F2[ip];
             }
             s = warp_sum(s);
             if (lane == 0) red[threadIdx.x >> 5] = s;
@@ -565,6 +568,7 @@ struct Ctx {
 #define FINT(s) (P.FI + (size_t)dof * ((s) - 1))
 #define KINT(s) (P.KI + (size_t)dof * ((s) - 1))
         if (P.mode == 2) {                       // evaluate_kernel!(out, kernel, F, t)
+            tix = P.tix0;
             eval(P.Fin, P.F_out);
             return;
         }
@@ -647,6 +651,7 @@ struct Ctx {
                 }
             }
             grid.sync();
+            tix = it;
             eval(FT(it), KT(it));                                                          // == initialize_K_temp! :155-166
             for (int e = gtid; e < dof; e += gthreads) { P.F_out[(size_t)it * dof + e] = FT(it)[e]; P.K_out[(size_t)it * dof + e] = KT(it)[e]; }
         }
@@ -669,6 +674,7 @@ struct Ctx {
             for (int it = n2 + 1; it <= n4 && status == MCT_OK; it++) {
                 const int i2 = it / 2;
                 const long long row = 1 + (long long)n2 * (blk + 1) + (it - n2 - 1);
+                tix = (long)row;
                 tp = clock64();
                 // update_Fuchs_parameters! :300-319 (compute_C3_mutable! :243-288), then update_F! with the stale K_temp[it]
                 // and the G matrices of the first evaluation, all on the lanes of the wavenumber's group

@@ -30,6 +30,9 @@ struct GridParams {
     unsigned long long *err;     // [2] rotating max-error words (bits of a non-negative double)
     double *F_out, *K_out;       // trajectory [nt][dof]  (mode 1/2: [dof])
     const double *Fin;           // mode 2: input F
+    // tagged dense kernels (TaggedActiveMCTKernel): collective trajectory [nt_c][Nk]; the evaluation at output time i is
+    // bilinear, sum W F[ik] Fc_i[ip].  tix0: time index of a mode-2 evaluation
+    const double *Fc; long nt_c, tix0;
     // k-sharding over GPUs (one process per GPU): rank r computes the line sums of lines L with L % world == r and stores
     // them straight into every rank's exchange buffer (peer memory over NVLink, IPC-mapped); 4 rotating buffers of
     // self-validating words, each rank re-arms its own copy.  world == 1: single GPU, Lsum only.

@@ -260,3 +260,32 @@ def active_evaluate(prefactor, J, V2, F):
             for l in range(abs(j - i) + 1, min(i + j - 1, Nk) + 1):
                 out[i - 1] += J[l - 1, j - 1, i - 1] * V2[l - 1, j - 1, i - 1] * F[j - 1] * F[l - 1]
     return out * prefactor                                             # :59
+
+
+# ---- TaggedActiveMCTKernel (src/Kernels/ActiveMCTKernel.jl:96-136), loop restatement for small Nk
+def tagged_active_tables(rho, k, wk, w0, Sk, dim=3):
+    from math import gamma, pi
+    k = np.asarray(k, dtype=np.float64); wk = np.asarray(wk, dtype=np.float64); Sk = np.asarray(Sk, dtype=np.float64)
+    Nk = len(k)
+    dk = k[1] - k[0]
+    surf = 2 * pi ** ((dim - 1) / 2) / gamma((dim - 1) / 2)
+    prefactor = rho * dk ** 2 / ((2 * pi) ** dim) * surf               # :98
+    mCk = 1 / rho * (1 - wk / (w0 * Sk))                               # :102
+    V2 = np.zeros((Nk, Nk, Nk)); J = np.zeros((Nk, Nk, Nk))
+    for i in range(1, Nk + 1):
+        for j in range(1, Nk + 1):
+            for l in range(abs(j - i) + 1, min(i + j - 1, Nk) + 1):   # :107
+                kk, q, p = k[i - 1], k[j - 1], k[l - 1]
+                V2[l - 1, j - 1, i - 1] = (mCk[l - 1] / (2 * kk) * (kk ** 2 + p ** 2 - q ** 2)) ** 2 * w0          # :112
+                J[l - 1, j - 1, i - 1] = 2 * p * q / ((2 * kk) ** (dim - 2)) * ((q + p - kk) * (kk + p - q) * (kk + q - p) * (kk + p + q)) ** ((dim - 3) / 2)
+    return prefactor, J, V2
+
+
+def tagged_active_evaluate(prefactor, J, V2, F_col, Fs):
+    Nk = len(Fs)
+    out = np.zeros(Nk)
+    for i in range(1, Nk + 1):                                         # :131-133
+        for j in range(1, Nk + 1):
+            for l in range(abs(j - i) + 1, min(i + j - 1, Nk) + 1):
+                out[i - 1] += J[l - 1, j - 1, i - 1] * V2[l - 1, j - 1, i - 1] * F_col[l - 1] * Fs[j - 1]
+    return out * prefactor

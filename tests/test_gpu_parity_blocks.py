@@ -190,3 +190,29 @@ def test_active_mct_kernel_eval_solve_and_steady_state_test_ActiveMCT():
     kb = pkg.ActiveMCTKernel(rho, k, wk, 0.8, Sk, 3)
     other = pkg.solve(pkg.MemoryEquation(1.0, 0.0, gamma, 0.0, Sk, np.zeros(Nk), kb), pkg.TimeDoublingSolver(**kw))
     assert abs(other.F.sum() - active.F.sum()) > 1e-3 * abs(active.F.sum())              # :32
+
+
+def test_tagged_active_mct_kernel_test_ActiveMCT_57_64():
+    """TaggedActiveMCTKernel chained on the device-resident collective solution: evaluation against the oracle's loops at
+    several times, and the reference's check that with w(k) = w0 = 1 it equals the passive tagged kernel (rtol 1e-5)."""
+    Nk = 20
+    p = P.hard_spheres(Nk, 0.51 * np.pi / 6, kmax=20.0)
+    rho, k, Sk = 0.51, p["k"], p["Sk"]
+    wk, w0 = np.ones(Nk), 1.0
+    gamma = k ** 2 * wk / Sk
+    kw = dict(N=8, dt=1e-6, t_max=1e4, tolerance=1e-10)
+    sol_act = pkg.solve(pkg.MemoryEquation(1.0, 0.0, gamma, 0.0, Sk, np.zeros(Nk), pkg.ActiveMCTKernel(rho, k, wk, w0, Sk, 3)),
+                        pkg.TimeDoublingSolver(**kw))
+    tk = pkg.TaggedActiveMCTKernel(rho, k, wk, w0, Sk, sol_act, 3)
+    pref, J, V2 = O.tagged_active_tables(rho, k, wk, w0, Sk, 3)
+    Fs = np.random.default_rng(1).random(Nk)
+    for tix in (0, 5, sol_act.F.shape[0] - 1):
+        ref = O.tagged_active_evaluate(pref, J, V2, sol_act.F[tix], Fs)
+        assert np.allclose(pkg.evaluate_kernel(tk, Fs, tix), ref, rtol=1e-12, atol=1e-300)
+    gamma2 = k ** 2 * w0
+    tsol_act = pkg.solve(pkg.MemoryEquation(1.0, 0.0, gamma2, 0.0, np.ones(Nk), np.zeros(Nk), tk), pkg.TimeDoublingSolver(**kw))
+    sol = pkg.solve(pkg.MemoryEquation(1.0, 0.0, gamma, 0.0, Sk, np.zeros(Nk), pkg.ModeCouplingKernel(rho, 1.0, 1.0, k, Sk)),
+                    pkg.TimeDoublingSolver(**kw))
+    tkp = pkg.TaggedModeCouplingKernel(rho, 1.0, 1.0, k, Sk, sol)
+    tsol = pkg.solve(pkg.MemoryEquation(1.0, 0.0, gamma2, 0.0, np.ones(Nk), np.zeros(Nk), tkp), pkg.TimeDoublingSolver(**kw))
+    assert tsol_act.F.sum() == pytest.approx(tsol.F.sum(), rel=1e-5)                     # test/test_ActiveMCT.jl:64
