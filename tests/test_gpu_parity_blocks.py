@@ -216,3 +216,18 @@ def test_tagged_active_mct_kernel_test_ActiveMCT_57_64():
     tkp = pkg.TaggedModeCouplingKernel(rho, 1.0, 1.0, k, Sk, sol)
     tsol = pkg.solve(pkg.MemoryEquation(1.0, 0.0, gamma2, 0.0, np.ones(Nk), np.zeros(Nk), tkp), pkg.TimeDoublingSolver(**kw))
     assert tsol_act.F.sum() == pytest.approx(tsol.F.sum(), rel=1e-5)                     # test/test_ActiveMCT.jl:64
+
+
+@pytest.mark.parametrize("Nk", [2, 3, 5, 33, 63, 130])
+@pytest.mark.parametrize("ns", [2, 4])
+def test_mc_eval_ragged_grid_sizes(ns, Nk):
+    """The line sums run on 4-wavenumber tiles with zero padding and only the d >= 0 / iq < ip halves are walked: sizes that
+    are not multiples of 4 (and the smallest grids) against the oracle's reference-order evaluation, with a random
+    NON-symmetric F so that nothing but the mirror property of the entries themselves is relied on."""
+    rho, m, k, Sk = mixture(ns, Nk=Nk)
+    rng = np.random.default_rng(100 * ns + Nk)
+    F = rng.random((Nk, ns, ns)) - 0.3
+    kern = pkg.MultiComponentModeCouplingKernel(rho, 0.7, m, k, Sk)
+    got = pkg.evaluate_kernel(kern, F)
+    ref = O.mc3d(rho, 0.7, m, k, Sk).evaluate(O._blocks(F))
+    assert np.max(np.abs(got - ref)) <= 1e-11 * np.abs(ref).max()
