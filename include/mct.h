@@ -65,7 +65,15 @@ MCT_API int mct_sc3d_tagged_create(mct_kernel_t *out, int device, int Nk, const 
                            const double *V3, long nt, const double *Fc_traj);
 MCT_API int mct_sc3d_tagged_create_from_sk(mct_kernel_t *out, int device, int Nk, double rho, double kBT, double m,
                                    const double *k_array, const double *Sk, long nt, const double *Fc_traj);
-/* Tagged kernel chained on the device-resident trajectory of a finished collective solve (no PCIe round trip). */
+/* The reference finds the collective solution at the time of an evaluation with `tDict[t]`, a Dict from the collective
+ * solve's output times to their index (:394, :436): a tagged solve on another time grid throws KeyError.  Pass
+ * get_t(sol) (nt doubles) here after one of the two constructors above and mct_equation_create checks every output time of
+ * the tagged solve against it (MCT_BAD_ARGUMENT on a mismatch); without it only the length of the trajectory is checked.
+ * Kernels chained on a device-resident solution (below) inherit the grid of that solve. */
+MCT_API int mct_kernel_set_collective_times(mct_kernel_t kernel, long nt, const double *t);
+/* Tagged kernel chained on the device-resident trajectory of a finished collective solve (no PCIe round trip).  The
+ * kernel reads that trajectory in place: mct_equation_destroy(collective) returns MCT_BAD_ARGUMENT until the kernel is
+ * destroyed. */
 MCT_API int mct_sc3d_tagged_create_from_equation(mct_kernel_t *out, int Nk, double rho, double kBT, double m, const double *k_array,
                                          const double *Sk, mct_equation_t collective);
 /* MultiComponentModeCouplingKernel3D from kernel.C (Vector{SMatrix}) and kernel.prefactor (Ns x Ns)
@@ -88,7 +96,8 @@ MCT_API int mct_active_tagged_create_from_equation(mct_kernel_t *out, int Nk, co
 MCT_API int mct_kernel_eval(mct_kernel_t kernel, const double *F, long t_index, double *out);
 /* n independent evaluations K_b = kernel(F_b), F and out are [n][dof] (parity tests, roofline measurement). */
 MCT_API int mct_kernel_eval_many(mct_kernel_t kernel, int n, const double *F, double *out, float *device_ms);
-/* A kernel handle must outlive every equation created on it (the equation uses the kernel's stream and scratch). */
+/* A kernel handle must outlive every equation created on it (the equation uses the kernel's stream, scratch and buffer
+ * pool): while such equations exist the call changes nothing and returns MCT_BAD_ARGUMENT. */
 MCT_API int mct_kernel_destroy(mct_kernel_t kernel);
 
 /* ---- TimeDoublingSolver: plug-in point #1, `solve(equation, solver)`  src/Solvers.jl:42-46 ---- */

@@ -51,7 +51,7 @@ class Coeffs(C.Structure):
 EXPORTS = [
     "mct_last_error", "mct_device_count", "mct_version", "mct_launch_count", "mct_sc3d_create", "mct_sc3d_create_from_sk",
     "mct_sc3d_tagged_create", "mct_sc3d_tagged_create_from_sk", "mct_sc3d_tagged_create_from_equation", "mct_mc3d_create",
-    "mct_ddim_create", "mct_kernel_eval", "mct_kernel_eval_many", "mct_kernel_destroy", "mct_td_output_len", "mct_td_solve",
+    "mct_ddim_create", "mct_kernel_eval", "mct_kernel_eval_many", "mct_kernel_destroy", "mct_kernel_set_collective_times", "mct_td_output_len", "mct_td_solve",
     "mct_equation_create", "mct_equation_solve", "mct_equation_download", "mct_equation_destroy", "mct_equation_solve_batch", "mct_equation_shard_prepare", "mct_equation_shard_connect",
     "mct_steady_state", "mct_msd3d_solve", "mct_equation_download_slice", "mct_equation_relaxation_times",
     "mct_mc3d_tagged_create_from_equation", "mct_msd_mc3d_solve", "mct_active_create", "mct_active_tagged_create_from_equation",
@@ -124,9 +124,12 @@ class MemoryKernel:
         return self.Nk * self.Ns * self.Ns
 
     def close(self):
+        """mct_kernel_destroy.  Refused (the handle stays valid) while equations created on this kernel are alive."""
         if self._h is not None and _lib is not None:
-            _lib.mct_kernel_destroy(self._h)
+            if _lib.mct_kernel_destroy(self._h) != MCT_OK:
+                raise MCTDeviceError(_lib.mct_last_error().decode())
             self._h = None
+            self._keep = ()
 
     def __del__(self):
         try:
@@ -205,7 +208,12 @@ def TaggedModeCouplingKernel(rho, kBT, m, k_array, Sk, sol, dims=3, device=0, ta
         V = [np.asfortranarray(v, dtype=np.float64) for v in tables]
         _check(L.mct_sc3d_tagged_create(C.byref(h), device, len(k), _p(k), _p(V[0]), _p(V[1]), _p(V[2]),
                                         C.c_long(Fc.shape[0]), _p(Fc)))
-    return MemoryKernel(h, len(k), 1, device)
+    kern = MemoryKernel(h, len(k), 1, device)
+    tc = getattr(sol, "t", None)
+    if tc is not None:                       # the keys of the reference's tDict (:394): checked against the tagged solve's grid
+        tc = _arr(tc)
+        _check(L.mct_kernel_set_collective_times(h, C.c_long(len(tc)), _p(tc)))
+    return kern
 
 
 class MSDKernel:
@@ -515,8 +523,10 @@ class _DeviceEquation:
         self._kernel = kernel      # the equation handle refers to the kernel handle: keep it alive as long as the equation
 
     def close(self):
+        """mct_equation_destroy.  Refused while a tagged kernel chained on this solution is alive."""
         if self._q is not None and _lib is not None:
-            _lib.mct_equation_destroy(self._q)
+            if _lib.mct_equation_destroy(self._q) != MCT_OK:
+                raise MCTDeviceError(_lib.mct_last_error().decode())
             self._q = None
         self._kernel = None
 

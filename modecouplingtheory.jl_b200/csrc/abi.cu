@@ -56,6 +56,9 @@ struct mct_kernel_s {
     long nt = 0;
     double *d_Fc = nullptr;
     bool owns_Fc = false;
+    std::vector<double> t_c;               // output times of the collective solution (the keys of the reference's tDict)
+    mct_equation_t borrowed_from = nullptr; // equation whose trajectory d_Fc points into (owns_Fc == false)
+    int live_equations = 0;                // equations created on this handle and not destroyed yet
     std::map<TeamLayout *, double *> slabs;  // team-layout tables per geometry
     double *d_scratch = nullptr; size_t scratch_doubles = 0;
     double *d_io = nullptr; size_t io_doubles = 0;
@@ -83,6 +86,8 @@ struct mct_equation_s {
     // k-sharding over GPUs: this rank's exchange buffer (IPC-exported) and the peers' mappings
     double *d_xshard = nullptr;
     void *peer_maps[kMaxShardRanks] = {};
+    int borrowers = 0;          // tagged / active kernels chained on this equation's device-resident trajectory
+    bool counted = false;       // included in kernel->live_equations
 };
 
 namespace mct {
@@ -297,6 +302,27 @@ static int count_blocks(const mct_td_options *o) {
     return n;
 }
 
+// t = dt/(4N) * it, exactly as allocate_results! forms it (src/TimeDoublingSolver.jl:431-434)
+static void output_times(const mct_td_options &o, int nblocks, std::vector<double> &t) {
+    const int N = o.N;
+    t.clear();
+    t.push_back(0.0);
+    double Dt = o.dt;
+    const double d0 = Dt / (4.0 * N);
+    for (int it = 1; it <= 2 * N; it++) t.push_back(d0 * it);
+    for (int b = 0; b < nblocks; b++, Dt *= 2.0) {
+        const double dl = Dt / (4.0 * N);
+        for (int it = 2 * N + 1; it <= 4 * N; it++) t.push_back(dl * it);
+    }
+}
+
+// RAII pair of CUDA events (no leak on the error paths of the timed launches)
+struct EventPair {
+    cudaEvent_t a = nullptr, b = nullptr;
+    cudaError_t create() { cudaError_t e = cudaEventCreate(&a); return e == cudaSuccess ? cudaEventCreate(&b) : e; }
+    ~EventPair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+};
+
 static int expand_coef(int kind, double lam, const double *arr, int Nk, double *dst, const char *name) {
     if (kind == 0) { for (int i = 0; i < Nk; i++) dst[i] = lam; return MCT_OK; }
     MCT_REQUIRE(kind == 1 && arr != nullptr, MCT_BAD_ARGUMENT, std::string("bad coefficient ") + name);
@@ -489,8 +515,9 @@ static int grid_setup(mct_equation_t q, mct_kernel_t h, int mode, const std::vec
     const size_t dfh = (mode == 0) ? (size_t)(2 * N + 1) * dof : 0;
     const size_t total = 6 * dof + 4 * ring + 7 * dof + 4 * dof + 6 * dof + lsum + dfh + 2 * traj + 40;
     MCT_CUDA(cudaMalloc(&q->d_gws, total * sizeof(double)));
-    MCT_CUDA(cudaMemset(q->d_gws, 0, total * sizeof(double)));
-    MCT_CUDA(cudaMemcpy(q->d_gws, coef_host.data(), 6 * dof * sizeof(double), cudaMemcpyHostToDevice));
+    cudaError_t e_init = cudaMemset(q->d_gws, 0, total * sizeof(double));
+    if (e_init == cudaSuccess) e_init = cudaMemcpy(q->d_gws, coef_host.data(), 6 * dof * sizeof(double), cudaMemcpyHostToDevice);
+    if (e_init != cudaSuccess) { cudaFree(q->d_gws); q->d_gws = nullptr; return cuda_fail(e_init, "grid_setup", __FILE__, __LINE__); }
     GridParams &g = q->gp;
     g = GridParams{};
     g.type = (h->type == K_MC3D) ? GK_MC3D : GK_DDIM; g.Nk = Nk; g.ns = ns; g.mode = mode;
@@ -517,16 +544,15 @@ static int grid_run(mct_equation_t q, long long *evals, int *status, float *devi
     MCT_CUDA(cudaSetDevice(h->device));
     cudaStream_t s = h->stream;
     MCT_CUDA(cudaMemsetAsync(q->gp.err, 0, 32 * sizeof(double), s));
-    cudaEvent_t e0, e1;
-    MCT_CUDA(cudaEventCreate(&e0)); MCT_CUDA(cudaEventCreate(&e1));
-    MCT_CUDA(cudaEventRecord(e0, s));
+    EventPair tm;
+    MCT_CUDA(tm.create());
+    MCT_CUDA(cudaEventRecord(tm.a, s));
     int rc = td_grid_launch(q->gp, h->n_sm, s);
     if (rc) return rc;
-    MCT_CUDA(cudaEventRecord(e1, s));
+    MCT_CUDA(cudaEventRecord(tm.b, s));
     MCT_CUDA(cudaStreamSynchronize(s));
     float ms = 0.f;
-    MCT_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    MCT_CUDA(cudaEventElapsedTime(&ms, tm.a, tm.b));
     if (device_ms) *device_ms = ms;
     int st = 0; long long ev = 0;
     MCT_CUDA(cudaMemcpy(&st, q->gp.status, sizeof(int), cudaMemcpyDeviceToHost));
@@ -543,6 +569,16 @@ static int grid_run(mct_equation_t q, long long *evals, int *status, float *devi
     if (evals) *evals = ev;
     if (status) *status = st;
     return st;
+}
+
+// A tagged / active kernel chained on the device-resident trajectory of a solved equation: it reads q->d_F in place, so the
+// equation must outlive it (mct_equation_destroy refuses while borrowers exist) and it inherits the equation's time grid
+// (the keys of the reference's tDict, src/Kernels/ModeCouplingKernels.jl:394).
+static void borrow_trajectory(mct_kernel_t h, mct_equation_t collective) {
+    h->nt = collective->nt; h->d_Fc = collective->d_F; h->owns_Fc = false;
+    h->borrowed_from = collective;
+    collective->borrowers++;
+    output_times(collective->opts, collective->nblocks, h->t_c);
 }
 
 }  // namespace mct
@@ -606,11 +642,13 @@ int mct_sc3d_tagged_create_from_equation(mct_kernel_t *out, int Nk, double rho, 
     MCT_REQUIRE(collective && collective->solved && collective->mode == 0, MCT_BAD_ARGUMENT,
                 "collective equation must be solved before a tagged kernel is chained on it");
     MCT_REQUIRE(collective->Nk == Nk, MCT_BAD_ARGUMENT, "collective solution has a different Nk");
+    MCT_REQUIRE(collective->ns == 1 && !collective->d_gws, MCT_BAD_ARGUMENT,
+                "the collective solution must be single-component (mixtures: mct_mc3d_tagged_create_from_equation)");
     int rc = new_handle(out, K_TAGGED3D, collective->kernel->device, Nk, k_array);
     if (rc) return rc;
     rc = setup_from_sk(*out, rho, kBT, m, Sk);
     if (rc) { mct_kernel_destroy(*out); *out = nullptr; return rc; }
-    (*out)->nt = collective->nt; (*out)->d_Fc = collective->d_F; (*out)->owns_Fc = false;
+    borrow_trajectory(*out, collective);
     return MCT_OK;
 }
 
@@ -640,6 +678,7 @@ int mct_mc3d_tagged_create_from_equation(mct_kernel_t *out, int s, double rho_al
     rc = upload_tables(h, V1.data(), V2.data(), V3.data());
     if (!rc) {
         h->nt = collective->nt; h->owns_Fc = true;
+        output_times(collective->opts, collective->nblocks, h->t_c);
         cudaError_t e = cudaMalloc(&h->d_Fc, (size_t)h->nt * Nk * sizeof(double));
         if (e != cudaSuccess) rc = cuda_fail(e, "mct_mc3d_tagged_create_from_equation", __FILE__, __LINE__);
     }
@@ -707,12 +746,22 @@ int mct_active_tagged_create_from_equation(mct_kernel_t *out, int Nk, const doub
                 MCT_BAD_ARGUMENT, "a solved scalar-valued collective equation with the same Nk is needed");
     int rc = mct_active_create(out, collective->kernel->device, Nk, k_array, prefactor, J, V2);
     if (rc) return rc;
-    (*out)->nt = collective->nt; (*out)->d_Fc = collective->d_F; (*out)->owns_Fc = false;
+    borrow_trajectory(*out, collective);
+    return MCT_OK;
+}
+
+int mct_kernel_set_collective_times(mct_kernel_t h, long nt, const double *t) {
+    MCT_REQUIRE(h && t && nt >= 1, MCT_BAD_ARGUMENT, "NULL argument to mct_kernel_set_collective_times");
+    MCT_REQUIRE(h->d_Fc != nullptr && nt == h->nt, MCT_BAD_ARGUMENT, "the kernel holds no collective trajectory of this length");
+    h->t_c.assign(t, t + nt);
     return MCT_OK;
 }
 
 int mct_kernel_destroy(mct_kernel_t h) {
     if (!h) return MCT_OK;
+    MCT_REQUIRE(h->live_equations == 0, MCT_BAD_ARGUMENT,
+                "mct_kernel_destroy: equations created on this kernel are still alive (destroy them first)");
+    if (h->borrowed_from) { h->borrowed_from->borrowers--; h->borrowed_from = nullptr; }
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->d_k); cudaFree(h->d_V1); cudaFree(h->d_Sk); cudaFree(h->d_C); cudaFree(h->d_W);
@@ -737,18 +786,17 @@ int mct_kernel_eval_many(mct_kernel_t h, int n, const double *F, double *out, fl
     if (rc) return rc;
     double *dF = h->d_io, *dO = h->d_io + (size_t)n * Nk;
     MCT_CUDA(cudaMemcpyAsync(dF, F, (size_t)n * Nk * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    cudaEvent_t e0, e1;
-    MCT_CUDA(cudaEventCreate(&e0)); MCT_CUDA(cudaEventCreate(&e1));
-    MCT_CUDA(cudaEventRecord(e0, h->stream));
+    EventPair tm;
+    MCT_CUDA(tm.create());
+    MCT_CUDA(cudaEventRecord(tm.a, h->stream));
     rc = sc3d_eval_launch(Nk, n, h->d_k, h->d_V1, h->d_V2, h->d_V3, dF, Nk, dF, h->d_scratch, dO, h->stream);
-    MCT_CUDA(cudaEventRecord(e1, h->stream));
+    MCT_CUDA(cudaEventRecord(tm.b, h->stream));
     if (rc) return rc;
     MCT_CUDA(cudaMemcpyAsync(out, dO, (size_t)n * Nk * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     MCT_CUDA(cudaStreamSynchronize(h->stream));
     float ms = 0.f;
-    MCT_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    MCT_CUDA(cudaEventElapsedTime(&ms, tm.a, tm.b));
     if (device_ms) *device_ms = ms;
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
     return MCT_OK;
 }
 
@@ -792,7 +840,7 @@ int mct_kernel_eval(mct_kernel_t h, const double *F, long t_index, double *out) 
 
 int mct_td_output_len(const mct_td_options *o, long *nt) {
     MCT_REQUIRE(o && nt, MCT_BAD_ARGUMENT, "NULL argument");
-    MCT_REQUIRE(o->N >= 1 && o->dt > 0 && o->t_max > 0, MCT_BAD_ARGUMENT, "bad solver options");
+    MCT_REQUIRE(o->N >= 2 && o->dt > 0 && o->t_max > 0, MCT_BAD_ARGUMENT, "bad solver options");   // same checks as mct_equation_create
     *nt = 1 + 2L * o->N + 2L * o->N * count_blocks(o);
     return MCT_OK;
 }
@@ -810,10 +858,21 @@ int mct_equation_create(mct_equation_t *out, mct_kernel_t h, const mct_coeffs *c
     mct_equation_t q = new mct_equation_s();
     q->kernel = h; q->Nk = Nk; q->opts = *o; q->nblocks = count_blocks(o);
     q->nt = 1 + 2L * o->N + 2L * o->N * q->nblocks;
-    if (h->type == K_TAGGED3D && h->nt < q->nt) {
-        delete q;
-        set_error("collective trajectory is shorter than this solve (tDict KeyError in the reference)");
-        return MCT_BAD_ARGUMENT;
+    if (h->d_Fc != nullptr) {
+        // the reference looks the collective solution up by time, `tDict[t]` (src/Kernels/ModeCouplingKernels.jl:394, 436):
+        // every output time of this solve must be a time of the collective solution, at the same index
+        bool ok = h->nt >= q->nt;
+        if (ok && !h->t_c.empty()) {
+            std::vector<double> t;
+            output_times(q->opts, q->nblocks, t);
+            for (long i = 0; ok && i < q->nt; i++) ok = (t[i] == h->t_c[i]);
+        }
+        if (!ok) {
+            delete q;
+            set_error("the time grid of this solve is not the time grid of the collective solution (tDict KeyError in the reference): "
+                      "use the same N, dt and a t_max that is not larger");
+            return MCT_BAD_ARGUMENT;
+        }
     }
     if (is_grid_kernel(h)) {
         const int ns = h->Ns;
@@ -833,6 +892,7 @@ int mct_equation_create(mct_equation_t *out, mct_kernel_t h, const mct_coeffs *c
         if (rc) { mct_equation_destroy(q); return rc; }
         q->gp.N = o->N; q->gp.nblocks = q->nblocks; q->gp.second_order = q->second_order;
         q->gp.dt0 = o->dt; q->gp.tol = o->tolerance; q->gp.max_iter = o->max_iterations;
+        h->live_equations++; q->counted = true;
         *out = q;
         return MCT_OK;
     }
@@ -867,6 +927,7 @@ int mct_equation_create(mct_equation_t *out, mct_kernel_t h, const mct_coeffs *c
     }
     if (e == cudaSuccess) e = cudaMemset(q->d_ring, 0, ring * sizeof(double));
     if (e == cudaSuccess) e = cudaMemset(q->d_status, 0, 64);
+    h->live_equations++; q->counted = true;
     if (e != cudaSuccess) { mct_equation_destroy(q); return cuda_fail(e, "mct_equation_create", __FILE__, __LINE__); }
     *out = q;
     return MCT_OK;
@@ -874,6 +935,9 @@ int mct_equation_create(mct_equation_t *out, mct_kernel_t h, const mct_coeffs *c
 
 int mct_equation_destroy(mct_equation_t q) {
     if (!q) return MCT_OK;
+    MCT_REQUIRE(q->borrowers == 0, MCT_BAD_ARGUMENT,
+                "mct_equation_destroy: a tagged kernel still reads this equation's device-resident trajectory (destroy it first)");
+    if (q->counted && q->kernel) q->kernel->live_equations--;
     if (q->kernel) cudaSetDevice(q->kernel->device);
     if (q->d_gws) { cudaFree(q->d_gws); q->d_F = nullptr; }
     for (int r = 0; r < kMaxShardRanks; r++) if (q->peer_maps[r]) cudaIpcCloseMemHandle(q->peer_maps[r]);
@@ -937,33 +1001,11 @@ int mct_equation_download(mct_equation_t q, double *t_out, double *F_out, double
     if (F_out) MCT_CUDA(cudaMemcpy(F_out, q->d_F, traj * sizeof(double), cudaMemcpyDeviceToHost));
     if (K_out) MCT_CUDA(cudaMemcpy(K_out, q->d_K, traj * sizeof(double), cudaMemcpyDeviceToHost));
     if (t_out) {
-        // t = dt/(4N) * it, exactly as allocate_results! forms it (src/TimeDoublingSolver.jl:431-434)
-        const int N = q->opts.N;
-        long p = 0;
-        t_out[p++] = 0.0;
-        double Dt = q->opts.dt;
-        const double d0 = Dt / (4.0 * N);
-        for (int it = 1; it <= 2 * N; it++) t_out[p++] = d0 * it;
-        for (int b = 0; b < q->nblocks; b++, Dt *= 2.0) {
-            const double dl = Dt / (4.0 * N);
-            for (int it = 2 * N + 1; it <= 4 * N; it++) t_out[p++] = dl * it;
-        }
+        std::vector<double> t;
+        output_times(q->opts, q->nblocks, t);
+        memcpy(t_out, t.data(), t.size() * sizeof(double));
     }
     return MCT_OK;
-}
-
-static void output_times(const mct_equation_s *q, std::vector<double> &t) {
-    // t = dt/(4N) * it, exactly as allocate_results! forms it (src/TimeDoublingSolver.jl:431-434)
-    const int N = q->opts.N;
-    t.clear();
-    t.push_back(0.0);
-    double Dt = q->opts.dt;
-    const double d0 = Dt / (4.0 * N);
-    for (int it = 1; it <= 2 * N; it++) t.push_back(d0 * it);
-    for (int b = 0; b < q->nblocks; b++, Dt *= 2.0) {
-        const double dl = Dt / (4.0 * N);
-        for (int it = 2 * N + 1; it <= 4 * N; it++) t.push_back(dl * it);
-    }
 }
 
 int mct_equation_download_slice(mct_equation_t q, long n_times, const long *times, int n_dofs, const int *dofs,
@@ -995,7 +1037,7 @@ int mct_equation_download_slice(mct_equation_t q, long n_times, const long *time
     }
     if (t_out) {
         std::vector<double> t;
-        output_times(q, t);
+        output_times(q->opts, q->nblocks, t);
         for (long i = 0; i < n_times; i++) t_out[i] = t[times ? times[i] : i];
     }
     return MCT_OK;
@@ -1007,7 +1049,7 @@ int mct_equation_relaxation_times(mct_equation_t q, int n_k, const int *ik, doub
     std::vector<double> F((size_t)q->nt * n_k), t;
     int rc = mct_equation_download_slice(q, 0, nullptr, n_k, ik, nullptr, F.data(), nullptr);
     if (rc) return rc;
-    output_times(q, t);
+    output_times(q->opts, q->nblocks, t);
     for (int j = 0; j < n_k; j++) {                                   // src/RelaxationTime.jl:14-39 per requested wavenumber
         double tau = INFINITY;
         const double f0 = F[j];

@@ -320,3 +320,43 @@ def test_streamed_download_of_mct_td_solve_equals_the_resident_solution(Nk, eta)
     t = np.empty(nt); F = np.empty((nt, Nk)); K = np.empty((nt, Nk))
     with pytest.raises(pkg.DomainError):
         pkg.api.solve_into(eq, pkg.TimeDoublingSolver(max_iterations=1, **kw), t, F, K)
+
+
+def test_tagged_solve_on_another_time_grid_is_a_keyerror_and_handles_are_refcounted():
+    """The reference looks the collective solution up with tDict[t] (src/Kernels/ModeCouplingKernels.jl:394, 436): a tagged
+    solve with another N or dt hits a KeyError.  The device pairs Fs(t) with Fc by output index, so mct_equation_create
+    must check the two time grids.  Also: handle lifetimes (a kernel cannot go while its equations live, a collective
+    equation cannot go while a tagged kernel reads its trajectory)."""
+    p = P.hard_spheres(64, 0.50)
+    kw = dict(N=8, dt=1e-6, t_max=1e-2, tolerance=1e-10)
+    sol, _ = gpu_solve(p, P.overdamped(p), **kw)
+    et = dict(alpha=0.0, beta=1.0, gamma=p["k"] ** 2, delta=0.0, F0=np.ones(64), dF0=np.zeros(64))
+
+    class HostSol: F = sol.F; t = sol.t
+    for tk in (pkg.TaggedModeCouplingKernel(p["rho"], 1.0, 1.0, p["k"], p["Sk"], sol),          # chained on the device solution
+               pkg.TaggedModeCouplingKernel(p["rho"], 1.0, 1.0, p["k"], p["Sk"], HostSol)):     # host trajectory + get_t(sol)
+        good, _ = gpu_solve(p, et, kernel=tk, **kw)
+        assert np.all(np.isfinite(good.F))
+        shorter, _ = gpu_solve(p, et, kernel=tk, **dict(kw, t_max=1e-4))     # a prefix of the collective grid is fine
+        assert np.array_equal(shorter.F, good.F[:shorter.F.shape[0]])
+        for bad in (dict(kw, dt=2e-6), dict(kw, N=4), dict(kw, t_max=1.0)):
+            with pytest.raises(AssertionError, match="tDict"):
+                gpu_solve(p, et, kernel=tk, **bad)
+        del good, shorter
+    # lifetimes
+    tk = pkg.TaggedModeCouplingKernel(p["rho"], 1.0, 1.0, p["k"], p["Sk"], sol)
+    with pytest.raises(pkg.MCTDeviceError, match="tagged kernel"):
+        sol._equation.close()
+    ts, _ = gpu_solve(p, et, kernel=tk, **kw)
+    with pytest.raises(pkg.MCTDeviceError, match="still alive"):
+        tk.close()
+    ts._equation.close()
+    tk.close()
+    sol._equation.close()
+    # a multi-component solution cannot feed the single-component tagged constructor
+    b = P.binary_mixture(Nk=64)
+    mk = pkg.MultiComponentModeCouplingKernel(b["rho"], 1.0, b["m"], b["k"], b["Sk"])
+    z = np.zeros((64, 2, 2))
+    msol = pkg.solve(pkg.MemoryEquation(1.0, 0.0, b["gamma"], z, b["Sk"], z, mk), pkg.TimeDoublingSolver(N=4, dt=1e-4, t_max=1e-3))
+    with pytest.raises(AssertionError, match="single-component"):
+        pkg.TaggedModeCouplingKernel(p["rho"], 1.0, 1.0, p["k"], p["Sk"], msol)

@@ -162,3 +162,57 @@ def test_active_kernel_equals_passive_kernel_test_ActiveMCT_16_22():
         b = O.active_tables(rho, p["k"], np.linspace(0.8, 1.2, 20), 0.9, p["Sk"], dim)
         assert a[0] == pytest.approx(b[0], rel=1e-15)
         assert np.allclose(a[1], b[1], rtol=1e-13, atol=0) and np.allclose(a[2], b[2], rtol=1e-13, atol=0)
+
+
+def test_ddim_critical_point_5d_test_dDimMCT_crit_pt_133_134():
+    """d = 5, Percus-Yevick direct correlation of Leutheusser (test/test_dDimMCT_crit_pt.jl:25-47, :100-134)."""
+    k = P.sf.wavenumber_grid(100)
+
+    def ck5d(eta):
+        T = 1 + 18 * eta + 6 * eta ** 2
+        Q0 = 1 / (120 * eta * (1 - eta) ** 3) * (1 - 33 * eta - 87 * eta ** 2 - 6 * eta ** 3 - T ** 1.5)
+        Q1 = -1 / (12 * (1 - eta) ** 3) * ((3 + 2 * eta) * T ** 0.5 + 3 + 19 * eta + 3 * eta ** 2)
+        Q2 = -T ** 0.5 / (24 * (1 - eta) ** 3) * (2 + 3 * eta + T ** 0.5)
+        c0 = -(-8 * Q2) ** 2
+        c1 = 120 * eta * Q0 ** 2
+        c3 = 20 * eta * (8 * Q0 * Q2 - 3 * Q1 ** 2)
+        c5 = -3 / 8 * eta * c0
+        return -(1 / k ** 10) * 8 * np.pi ** 2 * (
+            8 * (720 * c5 - 18 * c3 * k ** 2 + c1 * k ** 4)
+            + (-5760 * c5 + 144 * (c3 + 20 * c5) * k ** 2 - 8 * (c1 + 9 * c3 + 30 * c5) * k ** 4 + (3 * c0 + 4 * c1 + 6 * c3 + 8 * c5) * k ** 6) * np.cos(k)
+            + k * (-5760 * c5 + 48 * (3 * c3 + 20 * c5) * k ** 2 - (3 * c0 + 8 * (c1 + 3 * c3 + 6 * c5)) * k ** 4 + (c0 + c1 + c3 + c5) * k ** 6) * np.sin(k))
+
+    out = {}
+    for phi in (0.25, 0.26):
+        rho = 60 * phi / np.pi ** 2
+        ck = ck5d(phi)
+        Sk = 1 + rho * ck / (1 - rho * ck)
+        out[phi] = O.steady_state(O.ddim(rho, 1.0, 1.0, k, Sk, 5), k ** 2 / Sk, Sk, tolerance=1e-8)["F"].sum()
+    assert out[0.26] == pytest.approx(33.463940782589255, rel=RTOL)
+    assert out[0.25] < 1e-7
+
+
+def test_mc_with_one_species_equals_sc_kernel_test_MCTvsMCMCT_25():
+    p = P.hard_spheres(100, 0.50, rho_roundtrip=True)
+    F = np.random.default_rng(5).random(100)
+    sc = O.sc3d(p["rho"], 1.0, 1.0, p["k"], p["Sk"]).evaluate(F)
+    Sk1 = p["Sk"].reshape(100, 1, 1)
+    mc = O.mc3d([p["rho"]], 1.0, [1.0], p["k"], Sk1).evaluate(F)
+    nv = O.mc3d([p["rho"]], 1.0, [1.0], p["k"], Sk1, naive=True).evaluate(F)
+    assert np.allclose(mc, sc, rtol=RTOL, atol=0) and np.allclose(nv, sc, rtol=RTOL, atol=0)
+
+
+@pytest.mark.parametrize("ns", [3, 4])
+def test_mc_fast_kernel_equals_brute_force_for_3_and_4_species(ns):
+    """The reference pins its multi-component kernel with a brute-force triangle sum at Ns = 2 only
+    (test/test_MCMCT.jl:6-113, :192); the same cross-check here at the species counts of BASELINE config 4."""
+    diam = np.linspace(0.7, 1.0, ns)
+    cr = np.arange(1, ns + 1, dtype=float); cr /= cr.sum()
+    rho = 6 * 0.45 / (np.pi * np.sum(cr * diam ** 3)) * cr
+    m = np.linspace(1.0, 1.5, ns)
+    k = P.sf.wavenumber_grid(24)
+    Sk = P.sf.percus_yevick_mixture_sk(k, diam, rho)
+    F = O._blocks(np.random.default_rng(ns).random((24, ns, ns)))
+    a = O.mc3d(rho, 1.3, m, k, Sk).evaluate(F)
+    b = O.mc3d(rho, 1.3, m, k, Sk, naive=True).evaluate(F)
+    assert np.allclose(a, b, rtol=RTOL, atol=1e-13 * np.abs(b).max())
