@@ -4,7 +4,7 @@ at sizes the oracle needs minutes to hours for, so that the GPU tests and bench.
 without running the oracle at those sizes.
 
     python scripts/gen_fixtures.py c3            # config 3: Nk=1000, eta=0.5155 collective solve + tagged solve + tau_alpha  (~2.5 h, 1 core)
-    python scripts/gen_fixtures.py c5            # config 5: three sweep points at Nk=500 (below, near and above eta_c)
+    python scripts/gen_fixtures.py c5 [eta ...]  # config 5: three sweep points at Nk=500 (below, near and above eta_c)
     python scripts/gen_fixtures.py c4            # config 4: Ns=4 mixture at Nk=2000 on a short time axis
 
 The oracle (oracle/mct_oracle.c) is the C restatement of the reference in its own operation order; it is pinned on the
@@ -88,8 +88,8 @@ def gen_c3():
              **digest(rs, cols, pick_rows(nt), dict(Nk=1000, eta=0.5155, kpeak=kpeak, tau_alpha=taus)))
 
 
-def gen_c5():
-    for eta in (0.50, 0.5155, 0.52):
+def gen_c5(etas=(0.50, 0.5155, 0.52)):
+    for eta in etas:
         p = sc_problem(500, eta)
         cols, kpeak = sc_cols(p)
         t0 = time.time()
@@ -136,7 +136,7 @@ if __name__ == "__main__":
     if what == "c3":
         gen_c3()
     elif what == "c5":
-        gen_c5()
+        gen_c5(*([tuple(float(a) for a in sys.argv[2:])] if len(sys.argv) > 2 else []))
     elif what == "c4":
         gen_c4(*(json.loads(a) for a in sys.argv[2:]))
     else:
