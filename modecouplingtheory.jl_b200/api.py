@@ -20,7 +20,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "lib", "libmct_sm100a.so")
+# MCT_LIB selects another build of the same library (the instrumented MCT_PROFILE build of build.py, development only)
+_LIB_PATH = os.environ.get("MCT_LIB") or os.path.join(_HERE, "lib", "libmct_sm100a.so")
 _lib = None
 
 c_dp = C.POINTER(C.c_double)

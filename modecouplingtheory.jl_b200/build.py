@@ -8,8 +8,9 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
-OBJDIR = os.path.join(LIBDIR, "obj")
-LIB = os.path.join(LIBDIR, "libmct_sm100a.so")
+PROFILE = os.environ.get("MCT_PROFILE") == "1"      # instrumented build (phase counters), kept beside the product library
+OBJDIR = os.path.join(LIBDIR, "obj_prof" if PROFILE else "obj")
+LIB = os.path.join(LIBDIR, "libmct_sm100a_prof.so" if PROFILE else "libmct_sm100a.so")
 SOURCES = ["abi.cu", "layout.cu", "eval.cu", "td_sc.cu", "td_sc_k1.cu", "td_sc_k2.cu", "td_sc_k4.cu", "td_sc_k8.cu", "td_grid.cu", "msd.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -31,7 +32,7 @@ def build(force=False, verbose=False):
         return LIB
     os.makedirs(OBJDIR, exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    extra = ["-DMCT_PROFILE"] if os.environ.get("MCT_PROFILE") == "1" else []
+    extra = ["-DMCT_PROFILE"] if PROFILE else []
     extra += ["-Xptxas", "-v"] if verbose else []
 
     def compile_one(src):
