@@ -34,6 +34,7 @@ def build(force=False, verbose=False):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     extra = ["-DMCT_PROFILE"] if PROFILE else []
     extra += ["-Xptxas", "-v"] if verbose else []
+    extra += os.environ.get("MCT_NVCC_EXTRA", "").split()
 
     def compile_one(src):
         obj = os.path.join(OBJDIR, src.replace(".cu", ".o"))

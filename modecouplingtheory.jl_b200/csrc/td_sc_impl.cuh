@@ -27,8 +27,14 @@ namespace mct {
 
 namespace {
 
+#ifdef MCT_EXP_SLIM
+constexpr bool kSlim = true;
+#else
+constexpr bool kSlim = false;
+#endif
 constexpr unsigned long long kSentinel = 0xFFFFFFFFFFFFFFFFull;   // a NaN payload no arithmetic produces
-constexpr int kMaxTotWarps = 5;                                    // warps that scan the CTA totals -> G <= 160
+constexpr int kTotPerLane = 5;                                     // block totals per lane of the scanning warp -> G <= 160
+constexpr int kTotPieces = 10;                                     // 16-byte pieces of the totals [G][4] per lane (2G <= 320)
 
 
 extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -109,7 +115,8 @@ struct Team {
     int row0, nrows;             // rows owned by this CTA: [row0, row0 + nrows)
     int we0, we_n;               // first (warp,row) entry of this warp and how many it has
     int eb0, eb1;                // owner thread tid < nrows: entries of its row
-    int owner[KPT];              // owner CTA of the rows this thread finishes (k = tid*KPT + j)
+    int owner[KPT];              // owner CTA of the rows this thread finishes (k = j*kThreads + tid: consecutive lanes,
+                                 // consecutive rows -- conflict-free in shared memory, coalesced in the exchange buffer)
     // register-resident part of the tables: the 12 values of this lane for the first UR units of the warp
     double tab[UR > 0 ? UR : 1][kUV];
     int udesc[UR > 0 ? UR : 1];
@@ -217,7 +224,7 @@ struct Team {
             double *const sl0 = sLane + (size_t)warp * P.lane_cap * kUV * kLaneStride + (lane & 15);
             double *sl = sl0;
             const int US = P.US;
-            const int UG = P.U - UR - US;           // units that fit neither registers nor shared memory: from L2
+            const int UG = kSlim ? 0 : P.U - UR - US;           // units that fit neither registers nor shared memory: from L2
             Operands op, nop;
             int dn = (UR > 0) ? udesc[0] : (US > 0 ? sDesc[warp * US] : (UG > 0 ? __ldg(P.udesc + slab_base + (long long)warp * P.U) : 0));
             load_operands(dn, op);
@@ -302,7 +309,7 @@ struct Team {
     }
 
     // All-gather.  Owner threads publish `v` for their row; the last owner thread also publishes the CTA's block
-    // totals (B1,B2,B3).  Every thread collects the rows k = tid*KPT + j, every CTA scans the totals into sOff.
+    // totals (B1,B2,B3).  Every thread collects the rows k = j*kThreads + tid, every CTA scans the totals into sOff.
     //   X_USE_OFF: out = v_k - (rho_1[k] off_1 + rho_2[k] off_2 + rho_3[k] off_3) with the offsets of k's owner
     //   X_TRACK:   compare with fold (find_error, src/HelperFunctions.jl:55-64; F_old .= F, TimeDoublingSolver.jl:414)
     //   dst:       shared array receiving out (or nullptr)
@@ -311,13 +318,13 @@ struct Team {
                                             double (&out)[KPT]) {
         PROF(3);
         unsigned long long w[KPT];
-        if (P.G == 1) {
+        if (!kSlim && P.G == 1) {
             if (tid < nrows) sX[tid] = v;
             __syncthreads();
 #pragma unroll
-            for (int j = 0; j < KPT; j++) { const int k = tid * KPT + j; w[j] = (k < P.Nk) ? (unsigned long long)__double_as_longlong(sX[k]) : 0ull; }
+            for (int j = 0; j < KPT; j++) { const int k = j * kThreads + tid; w[j] = (k < P.Nk) ? (unsigned long long)__double_as_longlong(sX[k]) : 0ull; }
             PROF(5);
-        } else if (P.fabric == 1) {
+        } else if (!kSlim && P.fabric == 1) {
             // ---- cluster fabric: the team is one thread-block cluster; every CTA owns a copy of the exchange buffers in its
             //      shared memory and the publishers store straight into all of them (DSMEM).  Collecting is a local spin.
             epoch++;
@@ -348,7 +355,7 @@ struct Team {
             asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory");
 #pragma unroll
             for (int j = 0; j < KPT; j++) {
-                const int k = tid * KPT + j;
+                const int k = j * kThreads + tid;
                 w[j] = 0;
                 if (k < P.Nk) { while ((w[j] = ld_smem_relaxed_bits(lcur + 4 * P.G + k)) == kSentinel) { if (spin_check(t0, spins)) break; } }
             }
@@ -361,6 +368,11 @@ struct Team {
             }
             __syncthreads();
         } else {
+            // ---- L2 fabric: publish, bump the team's arrival counter, ONE thread polls it, everybody else waits at named
+            //      barrier 1 without issuing; then every thread loads its rows once (consecutive lanes, consecutive words) and
+            //      warp 0 loads the block totals and scans them while the rows are in flight.  Measured alternatives
+            //      (scripts/loop_bench.cu, profiles/loop_bench_r02.txt): polling the data words -- by every thread, by one
+            //      warp, with or without replicated buffers -- is slower or fragile under arrival skew.
             epoch++;
             double *cur = xbase + (size_t)(epoch & 3u) * P.xbuf_words, *clr = xbase + (size_t)((epoch + 2u) & 3u) * P.xbuf_words;
 #ifdef MCT_PROFILE
@@ -376,11 +388,7 @@ struct Team {
             const long long t0 = clock64();
             unsigned spins = 0;
             PROF(4);
-            // Arrival: every CTA bumps one counter after publishing and ONE thread per CTA polls it; everybody else waits
-            // at named barrier 1 without issuing.  (Polling the data words from many threads floods the ~100 hot L2
-            // lines with retries as soon as the CTAs drift apart: the L2 round trip then grows to microseconds and the
-            // exchange never recovers -- profiles/exchange_notes.md.)  The counter is only a hint: no fence orders it
-            // after the data, the words still validate themselves.
+            // The counter is only a hint: no fence orders it after the data, the words still validate themselves.
             if (warp == 0) {
                 __syncwarp();
                 if (lane == 0) {
@@ -394,50 +402,55 @@ struct Team {
             asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory");
             SNAP(20);
             PROF(5);
-            // one shot: rows for every thread, block totals for thread t < G; re-issue only what still shows the sentinel
-            const double *src = cur + 4 * P.G + tid * KPT;
-            const int nv = min(KPT, P.Nk - tid * KPT);     // rows of this thread that exist (<= 0: none)
-            unsigned long long t0w = 0, t1w = 0, t2w = 0, t3w = 0;
-            const double *tsrc = cur + 4 * tid;
-            const bool tot = tid < P.G;
-            if (KPT == 1) {
-                if (nv > 0) w[0] = ld_relaxed_bits(src);
-            } else {
+            // one shot: the rows of every thread; re-issue only what still shows the sentinel
+            const double *src = cur + 4 * P.G + tid;
 #pragma unroll
-                for (int j = 0; j < KPT; j += 2) if (j < nv) ld_relaxed2_bits(src + j, w[j], w[j + 1]);
+            for (int j = 0; j < KPT; j++) { w[j] = 0ull; if (j * kThreads + tid < P.Nk) w[j] = ld_relaxed_bits(src + j * kThreads); }
+            if (warp == 0) {
+                // block totals [G][4] in 16-byte pieces, coalesced; staged in the (idle) warp scratch so that lane l gets the
+                // kTotPerLane consecutive CTAs it scans
+                double *stg = sLane;
+                const int np = 2 * P.G;
+                unsigned long long pa[kTotPieces], pb[kTotPieces];
+#pragma unroll
+                for (int i = 0; i < kTotPieces; i++) { pa[i] = pb[i] = 0ull; if (i * 32 + lane < np) ld_relaxed2_bits(cur + 2 * (i * 32 + lane), pa[i], pb[i]); }
+                while (true) {
+                    bool again = false;
+#pragma unroll
+                    for (int i = 0; i < kTotPieces; i++)
+                        if (pa[i] == kSentinel || pb[i] == kSentinel) { ld_relaxed2_bits(cur + 2 * (i * 32 + lane), pa[i], pb[i]); again = true; }
+                    const bool stop = again && spin_check(t0, spins);
+                    if (!__any_sync(0xffffffffu, again) || __any_sync(0xffffffffu, stop)) break;
+                }
+#pragma unroll
+                for (int i = 0; i < kTotPieces; i++)
+                    if (i * 32 + lane < np) { stg[2 * (i * 32 + lane)] = bits2d(pa[i]); stg[2 * (i * 32 + lane) + 1] = bits2d(pb[i]); }
+                __syncwarp();
+                // exclusive prefix of the G block totals in a fixed order (identical in every CTA): serial inside a lane,
+                // warp scan of the lane sums
+                double l1[kTotPerLane], l2[kTotPerLane], l3[kTotPerLane];
+                double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+                const int c0 = lane * kTotPerLane;
+#pragma unroll
+                for (int i = 0; i < kTotPerLane; i++) {
+                    l1[i] = s1; l2[i] = s2; l3[i] = s3;
+                    if (c0 + i < P.G) { s1 += stg[4 * (c0 + i)]; s2 += stg[4 * (c0 + i) + 1]; s3 += stg[4 * (c0 + i) + 2]; }
+                }
+                double e1 = s1, e2 = s2, e3 = s3;
+                warp_inscan3(e1, e2, e3);
+                e1 -= s1; e2 -= s2; e3 -= s3;
+#pragma unroll
+                for (int i = 0; i < kTotPerLane; i++)
+                    if (c0 + i < P.G) { sOff[c0 + i] = e1 + l1[i]; sOff[GP + c0 + i] = e2 + l2[i]; sOff[2 * GP + c0 + i] = e3 + l3[i]; }
             }
-            if (tot) { ld_relaxed2_bits(tsrc, t0w, t1w); ld_relaxed2_bits(tsrc + 2, t2w, t3w); }
             while (true) {
                 bool again = false;
-                if (KPT == 1) {
-                    if (nv > 0 && w[0] == kSentinel) { w[0] = ld_relaxed_bits(src); again = true; }
-                } else {
 #pragma unroll
-                    for (int j = 0; j < KPT; j += 2)
-                        if (j < nv && (w[j] == kSentinel || (j + 1 < nv && w[j + 1] == kSentinel))) { ld_relaxed2_bits(src + j, w[j], w[j + 1]); again = true; }
-                }
-                if (tot) {
-                    if (t0w == kSentinel || t1w == kSentinel) { ld_relaxed2_bits(tsrc, t0w, t1w); again = true; }
-                    if (t2w == kSentinel || t3w == kSentinel) { ld_relaxed2_bits(tsrc + 2, t2w, t3w); again = true; }
-                }
+                for (int j = 0; j < KPT; j++)
+                    if (w[j] == kSentinel) { w[j] = ld_relaxed_bits(src + j * kThreads); again = true; }
                 if (!again || spin_check(t0, spins)) break;
             }
             SNAP(21);
-            if (tid < 32 * kMaxTotWarps && warp * 32 < P.G) {
-                // exclusive prefix of the G block totals in a fixed order: inside each warp of 32 CTAs, then the totals of
-                // the warps before (named barrier 2 among the <= 5 scanning warps)
-                const double b1 = bits2d(t0w), b2 = bits2d(t1w), b3 = bits2d(t2w);
-                double s1 = b1, s2 = b2, s3 = b3;
-                warp_inscan3(s1, s2, s3);
-                if (lane == 31) { sWT[warp] = s1; sWT[8 + warp] = s2; sWT[16 + warp] = s3; }
-                const int nscan = ((P.G + 31) >> 5) * 32;
-                asm volatile("bar.sync 2, %0;" ::"r"(nscan) : "memory");
-                double w1 = 0.0, w2 = 0.0, w3 = 0.0;
-                for (int ww = 0; ww < warp; ww++) { w1 += sWT[ww]; w2 += sWT[8 + ww]; w3 += sWT[16 + ww]; }
-                // (an inclusive scan minus the own value is not bit-identical to an exclusive scan, but it is the
-                //  same numbers in every CTA, which is all that is required)
-                if (tot) { sOff[tid] = w1 + (s1 - b1); sOff[GP + tid] = w2 + (s2 - b2); sOff[2 * GP + tid] = w3 + (s3 - b3); }
-            }
             __syncthreads();
         }
         PROF(6);
@@ -446,7 +459,7 @@ struct Team {
         int pred = 0;
 #pragma unroll
         for (int j = 0; j < KPT; j++) {
-            const int k = tid * KPT + j;
+            const int k = j * kThreads + tid;
             double f = bits2d(w[j]);
             if (k < P.Nk) {
 #ifdef MCT_PROFILE
@@ -470,73 +483,6 @@ struct Team {
         SNAP(23);
         return any;
     }
-
-#ifdef MCT_PROFILE
-    // bare-bones copy of scripts/xchg_bench4.cu 'packed' for bisection
-    __device__ __forceinline__ unsigned long long exchange_min(double v) {
-        epoch++;
-        double *cur = xbase + (size_t)(epoch & 3u) * P.xbuf_words, *clr = xbase + (size_t)((epoch + 2u) & 3u) * P.xbuf_words;
-        const int pub = (P.dbg & 32) ? nrows - 1 : 0;
-        const bool snap = false;
-        if (tid < nrows) st_relaxed(cur + 4 * P.G + row0 + tid, v);
-        if (tid == pub) { st_relaxed2(cur + 4 * cta, v, v); st_relaxed2(cur + 4 * cta + 2, v, 0.0); }
-        if (tid < nrows) st_relaxed_bits(clr + 4 * P.G + row0 + tid, kSentinel);
-        if (tid == pub) { st_relaxed2_bits(clr + 4 * cta, kSentinel, kSentinel); st_relaxed2_bits(clr + 4 * cta + 2, kSentinel, kSentinel); }
-        if (P.dbg & 256) asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory"); else __syncthreads();
-        const long long t0 = clock64();
-        if (P.dbg & 512) __nanosleep(300); else { while (clock64() - t0 < 300) {} }
-        const double *src = cur + 4 * P.G + 4 * tid;
-        unsigned long long w0 = 0, w1 = 0, w2 = 0, w3 = 0;
-        const int nv = min(4, P.Nk - 4 * tid);
-        unsigned spins = 0;
-        if (nv > 0) ld_relaxed2_bits(src, w0, w1);
-        if (nv > 2) ld_relaxed2_bits(src + 2, w2, w3);
-        bool again = true;
-        while (again) {
-            again = false;
-            if (nv > 0 && (w0 == kSentinel || (nv > 1 && w1 == kSentinel))) { ld_relaxed2_bits(src, w0, w1); again = true; }
-            if (nv > 2 && (w2 == kSentinel || (nv > 3 && w3 == kSentinel))) { ld_relaxed2_bits(src + 2, w2, w3); again = true; }
-            if ((P.dbg & 64) && again && spin_check(t0, spins)) break;
-        }
-        unsigned long long a = 0, b = 0, c = 0, d = 0;
-        if (tid < P.G) {
-            const double *ts = cur + 4 * tid;
-            ld_relaxed2_bits(ts, a, b); ld_relaxed2_bits(ts + 2, c, d);
-            while (a == kSentinel || b == kSentinel || c == kSentinel || d == kSentinel) {
-                if (a == kSentinel || b == kSentinel) ld_relaxed2_bits(ts, a, b);
-                if (c == kSentinel || d == kSentinel) ld_relaxed2_bits(ts + 2, c, d);
-                if ((P.dbg & 64) && spin_check(t0, spins)) break;
-            }
-        }
-        if (P.dbg & 128) {
-            long long ta = clock64();
-            prof[14] += ta - t0;
-            if (snap) { long long g; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g)); prof[20] = g; }
-            if (tid < 32 * kMaxTotWarps && warp * 32 < P.G) {
-                const double b1 = bits2d(a), b2 = bits2d(b), b3 = bits2d(c);
-                double s1 = b1, s2 = b2, s3 = b3;
-                warp_inscan3(s1, s2, s3);
-                if (tid < P.G) { sOff[tid] = s1 - b1; sOff[GP + tid] = s2 - b2; sOff[2 * GP + tid] = s3 - b3; }
-                if (lane == 31) { sWT[warp] = s1; sWT[8 + warp] = s2; sWT[16 + warp] = s3; }
-            }
-            long long tb = clock64(); prof[15] += tb - ta;
-            __syncthreads();
-            long long tc = clock64(); prof[16] += tc - tb;
-            cta_offsets(cta, myoff1, myoff2, myoff3);
-            double o1, o2, o3;
-            cta_offsets(owner[0], o1, o2, o3);
-            w0 += (unsigned long long)(o1 + o2 + o3);
-            long long td = clock64(); prof[17] += td - tc;
-            const int r = __syncthreads_or((int)(w0 & 1));
-            long long te = clock64(); prof[18] += te - td;
-            if (snap) { long long g; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g)); prof[21] = g; }
-            return r + w0 + w1 + w2 + w3 + a + b + c + d;
-        }
-        __syncthreads();
-        __syncthreads();
-        return w0 + w1 + w2 + w3 + a + b + c + d;
-    }
-#endif
 
     // ------------------------------------------------------------------------------------------ per-equation setup
     __device__ __forceinline__ void load_tables(const EqDev &E) {
@@ -571,7 +517,7 @@ struct Team {
         double fold[KPT], out[KPT];
 #pragma unroll
         for (int j = 0; j < KPT; j++) {
-            const int kk = tid * KPT + j;
+            const int kk = j * kThreads + tid;
             fold[j] = (kk < P.Nk) ? E.F0[kk] : 0.0;              // Fold = copy(F0) :68
             if (kk < P.Nk) sF2[kk] = fold[j];
         }
@@ -616,8 +562,7 @@ struct Team {
 #ifdef MCT_PROFILE
         {   // isolated cost of the two building blocks (cycles of thread 0, 2000 repetitions each)
             long long c0 = clock64();
-            if (P.dbg & 16) { unsigned long long acc = 0; for (int i = 0; i < 2000; i++) acc += exchange_min(1.0 + i); if (acc == 12345) prof[13] = 1; }
-            else for (int i = 0; i < 2000; i++) exchange(1.0 + i, 0.0, 0.0, 0.0, 0, fold, nullptr, out);
+            for (int i = 0; i < 2000; i++) exchange(1.0 + i, 0.0, 0.0, 0.0, 0, fold, nullptr, out);
             long long c1 = clock64();
             for (int i = 0; i < 2000; i++) { double l1, l2, l3; eval_rows(E.tab, l1, l2, l3); __syncthreads(); }
             long long c2 = clock64();
@@ -712,7 +657,7 @@ struct Team {
             exchange(c2 / c1, 0.0, 0.0, 0.0, 0, fold, nullptr, out);
 #pragma unroll
             for (int j = 0; j < KPT; j++) {
-                const int kk = tid * KPT + j;
+                const int kk = j * kThreads + tid;
                 if (kk < P.Nk) {
                     const double kv = E.kvec[kk];
                     sRho[kk] = out[j] * kv; sRho[NkP + kk] = out[j] / (kv * kv * kv); sRho[2 * NkP + kk] = out[j] / kv;
@@ -856,7 +801,7 @@ __global__ void __launch_bounds__(kThreads, 1) td_sc_kernel(const SolveParams P)
         T.eb0 = (T.tid < T.nrows) ? eb[T.tid / kRB] : 0;
         T.eb1 = (T.tid < T.nrows) ? eb[T.tid / kRB + 1] : 0;
 #pragma unroll
-        for (int j = 0; j < KPT; j++) { const int k = T.tid * KPT + j; T.owner[j] = (k < P.Nk) ? P.row_owner[k] : 0; }
+        for (int j = 0; j < KPT; j++) { const int k = j * kThreads + T.tid; T.owner[j] = (k < P.Nk) ? P.row_owner[k] : 0; }
 #pragma unroll
         for (int u = 0; u < UR; u++) T.udesc[u] = (u < P.U) ? P.udesc[T.slab_base + (long long)T.warp * P.U + u] : 0;
         if (T.lane < P.US) ((int *)(smem_raw + P.so.desc))[T.warp * P.US + T.lane] = P.udesc[T.slab_base + (long long)T.warp * P.U + UR + T.lane];
