@@ -212,25 +212,30 @@ static int env_int(const char *name, int dflt) {
     return (v && *v) ? atoi(v) : dflt;
 }
 
-struct Residency { int UR, US, lane_cap; };
+struct Residency { int UR, UT, US, lane_cap; };
 
 // How the U units of every warp are kept: UR in registers (a kernel instantiation), US in shared memory, rest in L2.
 static Residency choose_residency(const TeamLayout &L, size_t smem_optin, int fabric) {
     Residency r;
     // 24 registers per register-resident unit; the instantiation that finishes 4 rows per thread (Nk > 512) has 28
     // fewer registers to spare (measured: 2 units there, 4 otherwise, keeps spills out of the kernel)
+    // Tensor memory first: a warp owns 256 of the SM's 512 columns in its lane quarter = 10 units of 24 columns, read at
+    // ~2.7x the shared-memory rate and without taking registers (scripts/tmem_bench.cu).  Then registers (24 per unit; the
+    // instantiations that finish 4 or 8 rows per thread have fewer to spare), then shared memory, the rest streams from L2.
+    const int utmax = env_int("MCT_TMEM", 1) ? std::min(10, env_int("MCT_MAX_TMEM_UNITS", 10)) : 0;
     const int urmax = std::min(td_sc_max_reg_units(L.Nk), env_int("MCT_MAX_REG_UNITS", td_sc_max_reg_units(L.Nk)));
     r.UR = 0;
-    for (int ur : {2, 4}) if (ur <= urmax) { r.UR = ur; if (ur >= L.U) break; }
+    if (L.U > utmax) for (int ur : {2, 4}) if (ur <= urmax && ur <= L.U) { r.UR = ur; if (ur >= L.U - utmax) break; }
+    r.UT = std::min(L.U - r.UR, utmax);
     r.lane_cap = std::max(1, L.went_max);               // one scratch column set per (warp, row block) entry
     SolveParams P{};
-    P.Nk = L.Nk; P.G = L.G; P.rows_max = L.rows_max; P.ent_max = L.ent_max; P.lane_cap = r.lane_cap; P.US = 0;
+    P.Nk = L.Nk; P.G = L.G; P.rows_max = L.rows_max; P.ent_max = L.ent_max; P.lane_cap = r.lane_cap; P.U = L.U; P.UT = r.UT; P.US = 0;
     P.fabric = fabric; P.xbuf_words = L.xbuf_words;
-    const int want = std::max(0, L.U - r.UR);
+    const int want = std::max(0, L.U - r.UR - r.UT);
     const size_t fixed = td_sc_smem_bytes(P);
     const size_t per_unit = (size_t)kWarps * (kUV * 32 * 8 + 4);
     const int cap = fixed + 64 < smem_optin ? (int)((smem_optin - fixed - 64) / per_unit) : 0;
-    r.US = std::min(std::min(want, cap), 32);           // (the descriptors of the shared-memory units are loaded by one warp)
+    r.US = std::min(want, cap);
     return r;
 }
 
@@ -380,7 +385,7 @@ static int run_batch(int n, mct_equation_t *eqs, int mode, double tol, long long
     P.Nk = h0->Nk; P.G = L->G; P.N = eqs[0]->opts.N; P.nblocks = eqs[0]->nblocks; P.n_eq = n; P.nteams = nteams;
     P.second_order = eqs[0]->second_order;
     P.dt0 = eqs[0]->opts.dt; P.tol = tol; P.max_iter = max_iter;
-    P.U = L->U; P.UR = res.UR; P.US = res.US; P.lane_cap = res.lane_cap;
+    P.U = L->U; P.UR = res.UR; P.UT = res.UT; P.US = res.US; P.lane_cap = res.lane_cap;
     P.rows_max = L->rows_max; P.rb_max = L->rb_max; P.ent_max = L->ent_max;
     P.udesc = L->d_udesc; P.cta_meta = L->d_cta_meta; P.ent_begin = L->d_ent_begin; P.warp_ent = L->d_warp_ent; P.row_owner = L->d_row_owner;
     P.xbuf_words = L->xbuf_words; P.fabric = fabric;
@@ -397,8 +402,8 @@ static int run_batch(int n, mct_equation_t *eqs, int mode, double tol, long long
         P.nteams = nteams;
     }
     if (env_int("MCT_VERBOSE", 0))
-        fprintf(stderr, "[mct] Nk=%d sym=%d n_eq=%d: teams=%d x G=%d, U=%d units/warp (%d regs, %d smem, %d L2), rows/CTA<=%d, entries/warp<=%d, smem=%zu B, fabric=%s\n",
-                P.Nk, h0->sym, n, nteams, P.G, P.U, std::min(P.U, P.UR), P.US, std::max(0, P.U - P.UR - P.US), P.rows_max, L->went_max, td_sc_smem_bytes(P), P.fabric ? "cluster/DSMEM" : (P.G > 1 ? "L2" : "none"));
+        fprintf(stderr, "[mct] Nk=%d sym=%d n_eq=%d: teams=%d x G=%d, U=%d units/warp (%d regs, %d tmem, %d smem, %d L2), rows/CTA<=%d, entries/warp<=%d, smem=%zu B, fabric=%s\n",
+                P.Nk, h0->sym, n, nteams, P.G, P.U, std::min(P.U, P.UR), P.UT, P.US, std::max(0, P.U - P.UR - P.UT - P.US), P.rows_max, L->went_max, td_sc_smem_bytes(P), P.fabric ? "cluster/DSMEM" : (P.G > 1 ? "L2" : "none"));
 
     // communication scratch: exchange buffers and queue mailboxes (all slots armed with the sentinel = 0xFF bytes),
     // queue, abort flag, equation table
@@ -447,8 +452,8 @@ static int run_batch(int n, mct_equation_t *eqs, int mode, double tol, long long
         static const char *nm[kProfSlots] = {"stream+warp reduce", "barrier", "row sums+prefix", "F_loc", "publish+delay", "collect", "offset scan+barrier",
                                             "apply+or-barrier", "between", "step-local", "=exchange alone", "=eval alone", "=eval+exchange", "-", "x:loads", "x:scan", "x:sync", "x:offsets", "x:or-barrier", "-", "-", "-", "-", "-", "-", "-", "-", "-", "-", "-", "TOTAL cycles", "TOTAL ns"};
         const int ctas[3] = {0, P.G / 2, P.G - 1};
-        fprintf(stderr, "[mct profile] Nk=%d G=%d nteams=%d U=%d UR=%d US=%d; thread 0 of CTA %d / %d / %d (team 0)\n", P.Nk, P.G, nteams,
-                P.U, P.UR, P.US, ctas[0], ctas[1], ctas[2]);
+        fprintf(stderr, "[mct profile] Nk=%d G=%d nteams=%d U=%d UR=%d UT=%d US=%d; thread 0 of CTA %d / %d / %d (team 0)\n", P.Nk, P.G, nteams,
+                P.U, P.UR, P.UT, P.US, ctas[0], ctas[1], ctas[2]);
         for (int i = 0; i < kProfSlots; i++) {
             if (nm[i][0] == '-') continue;
             fprintf(stderr, "   %-20s", nm[i]);

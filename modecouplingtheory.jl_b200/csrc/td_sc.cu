@@ -10,7 +10,7 @@ void *td_sc_entry_k1(int UR);
 void *td_sc_entry_k2(int UR);
 void *td_sc_entry_k4(int UR);
 void *td_sc_entry_k8(int UR);
-SmemOffsets td_sc_plan_smem(int Nk, int G, int rows_max, int ent_max, int lane_cap, int US, int fabric, int xbuf_words) {
+SmemOffsets td_sc_plan_smem(int Nk, int G, int rows_max, int ent_max, int lane_cap, int U, int US, int fabric, int xbuf_words) {
     SmemOffsets p;
     size_t o = 0;
     const int NkP = even_up(Nk), NkF = even_up(Nk + 2 * kFPad);
@@ -31,7 +31,7 @@ SmemOffsets td_sc_plan_smem(int Nk, int G, int rows_max, int ent_max, int lane_c
     p.eq = (unsigned)o; o += (sizeof(EqDev) + 15) & ~(size_t)15;
     o = (o + 15) & ~(size_t)15;
     p.xd = (unsigned)o; o += (fabric == 1) ? (size_t)4 * xbuf_words * 8 : 0;     // cluster fabric: the exchange buffers live here
-    p.desc = (unsigned)o; o += (size_t)even_up(kWarps * US) * 4;
+    p.desc = (unsigned)o; o += (size_t)kWarps * (U + 2) * 8;        // operand addresses of every unit (int2)
     o = (o + 15) & ~(size_t)15;
     p.tab = (unsigned)o; o += (size_t)kWarps * US * kUV * 32 * 8;
     p.total = (unsigned)o;
@@ -39,7 +39,7 @@ SmemOffsets td_sc_plan_smem(int Nk, int G, int rows_max, int ent_max, int lane_c
 }
 
 
-size_t td_sc_smem_bytes(const SolveParams &P) { return td_sc_plan_smem(P.Nk, P.G, P.rows_max, P.ent_max, P.lane_cap, P.US, P.fabric, P.xbuf_words).total; }
+size_t td_sc_smem_bytes(const SolveParams &P) { return td_sc_plan_smem(P.Nk, P.G, P.rows_max, P.ent_max, P.lane_cap, P.U, P.US, P.fabric, P.xbuf_words).total; }
 
 int td_sc_max_reg_units(int Nk) { return (Nk > 2 * kThreads) ? 2 : 4; }
 
@@ -57,7 +57,7 @@ int td_sc_launch(const SolveParams &P, cudaStream_t stream) {
     MCT_REQUIRE(fn != nullptr, MCT_BAD_ARGUMENT, "internal: no kernel instantiation for this UR");
     MCT_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     SolveParams Pc = P;
-    Pc.so = td_sc_plan_smem(P.Nk, P.G, P.rows_max, P.ent_max, P.lane_cap, P.US, P.fabric, P.xbuf_words);
+    Pc.so = td_sc_plan_smem(P.Nk, P.G, P.rows_max, P.ent_max, P.lane_cap, P.U, P.US, P.fabric, P.xbuf_words);
     void *args[] = {(void *)&Pc};
     dim3 grid(P.nteams * P.G), block(kThreads);
     if (P.fabric == 1) {

@@ -32,7 +32,8 @@ struct SolveParams {
     // layout geometry shared by every equation of the launch (layout.cuh)
     int U;                      // units per warp (a unit = 32 positions x 4 rows, layout.cuh)
     int UR;                     // units per warp resident in registers (selects the kernel instantiation)
-    int US;                     // units per warp resident in shared memory; the remaining U-UR-US stream from L2
+    int UT;                     // units per warp resident in tensor memory (24 of the warp's 256 columns each, <= 10)
+    int US;                     // units per warp resident in shared memory; the remaining U-UR-UT-US stream from L2
     int rows_max, rb_max, ent_max, lane_cap;
     const int *udesc, *cta_meta, *ent_begin, *warp_ent, *row_owner;
     // team communication
@@ -54,7 +55,7 @@ struct SolveParams {
 };
 
 constexpr int kProfSlots = 32;
-constexpr int kLaneStride = 17;                                    // padded column of the warp scratch: 16 half-warp partials
+constexpr int kLaneStride = 33;                                    // padded column of the warp scratch: 32 lane partials
 enum { OWN_K = 0, OWN_F0, OWN_AL, OWN_BE, OWN_GA, OWN_DE, OWN_K0, kOwnFields };   // per-row constants of the owner, in shared memory
 __host__ __device__ inline int even_up(int n) { return (n + 1) & ~1; }
 

@@ -27,11 +27,6 @@ namespace mct {
 
 namespace {
 
-#ifdef MCT_EXP_SLIM
-constexpr bool kSlim = true;
-#else
-constexpr bool kSlim = false;
-#endif
 constexpr unsigned long long kSentinel = 0xFFFFFFFFFFFFFFFFull;   // a NaN payload no arithmetic produces
 constexpr int kTotPerLane = 5;                                     // block totals per lane of the scanning warp -> G <= 160
 constexpr int kTotPieces = 10;                                     // 16-byte pieces of the totals [G][4] per lane (2G <= 320)
@@ -77,6 +72,27 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+// ---- tensor memory as a per-warp scratchpad for table values (no MMA involved): warp w owns the 32-lane quarter w % 4 and
+//      the column half w / 4 of the CTA's 512 columns; a unit is 24 columns (12 doubles per lane).  Measured (scripts/
+//      tmem_bench.cu): 339 B/clk/SM against 127 B/clk/SM for the same values in shared memory, bit-exact round trip.
+__device__ __forceinline__ void tmem_ld24(unsigned taddr, unsigned (&r)[24]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+                   "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23])
+                 : "r"(taddr + 16));
+}
+__device__ __forceinline__ void tmem_st8(unsigned taddr, const unsigned (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+constexpr int kTmemCols = 512;                    // the whole tensor memory of the SM (one CTA per SM)
+constexpr int kTmemUnitCols = 2 * kUV;            // 24 columns of 32 bits = 12 doubles per lane
+
 #ifdef MCT_PROFILE
 #define PROF(i) do { long long now__ = clock64(); prof[i] += now__ - tlast; tlast = now__; } while (0)
 #else
@@ -103,7 +119,6 @@ struct Team {
 #define sX ((double *)(smem_raw + P.so.X))
 #define sScan ((double *)(smem_raw + P.so.scan))
 #define sTab ((double *)(smem_raw + P.so.tab))
-#define sDesc ((int *)(smem_raw + P.so.desc))
 #define sAbort ((volatile int *)(smem_raw + P.so.misc))
 #define sXD ((double *)(smem_raw + P.so.xd))
     // identity
@@ -119,12 +134,12 @@ struct Team {
                                  // consecutive rows -- conflict-free in shared memory, coalesced in the exchange buffer)
     // register-resident part of the tables: the 12 values of this lane for the first UR units of the warp
     double tab[UR > 0 ? UR : 1][kUV];
-    int udesc[UR > 0 ? UR : 1];
     // exchange
     double *xbase, *qbase;
     unsigned epoch, qepoch;
     double myoff1, myoff2, myoff3;   // offsets of this CTA from the last exchange
     long long slab_base;         // first slot of this CTA in the team layout
+    unsigned tbase;              // tensor-memory address of this warp's first table unit
 #ifdef MCT_PROFILE
     long long prof[kProfSlots], tlast;
 #endif
@@ -172,40 +187,36 @@ struct Team {
 
     // ------------------------------------------------------------------------------------------ kernel evaluation
     // One unit (layout.cuh): 32 positions x 4 rows.  Every lane loads its single operand and the 4 consecutive window
-    // operands, forms the 4 products and feeds 12 FMAs with the 12 table values it owns.  When the unit starts a new
-    // (warp, row block) entry the 12 finished partials are parked in the warp scratch first (warp-uniform, rare).
-    // The operands of the NEXT unit are loaded before the arithmetic of this one (op/nop), otherwise every row waits
-    // for its own shared-memory load.
-    // park the 12 lane partials of a finished entry: one butterfly step first, so that only 16 values per column go to
-    // shared memory (halves the scratch, which buys one more shared-memory-resident table unit at Nk = 1000)
-    __device__ __forceinline__ void park(const double (&acc)[kUV], double *sl) const {
-#pragma unroll
-        for (int v = 0; v < kUV; v++) {
-            const double x = acc[v] + __shfl_xor_sync(0xffffffffu, acc[v], 16);
-            if (lane < 16) sl[v * kLaneStride] = x;
-        }
-    }
+    // operands, forms the 4 products and feeds 12 FMAs with the 12 table values it owns.  The loop is bound by the number of
+    // instructions a warp has to issue (two warps per scheduler, ~0.5 IPC), so everything that does not depend on the iterate
+    // is decoded once per equation: sUA holds, per (warp, unit), the shared-memory byte addresses of lane 0's operands
+    //     x = &S[a0],   y = &W[w0 - kFPad] | 1 (window index decreases with the lane) | 2 (first unit of a new entry).
+    // Rows that do not exist in a trailing row block have zero table values, their FMAs add zero (no branches).  The
+    // operands of unit u+1 and the addresses of unit u+2 are loaded before the arithmetic of unit u.
+    // When a unit starts a new (warp, row block) entry the 12 lane partials of the finished one are parked as they are in
+    // the warp scratch [entry][12][kLaneStride] (warp-uniform, rare); the lanes add the columns after the last unit.
     struct Operands { double f1, w[kRB]; };
-    __device__ __forceinline__ void load_operands(int d, Operands &o) const {
-        const double *S = (d & kUSwap) ? (const double *)sF2 : sF1, *W = (d & kUSwap) ? sF1 : (const double *)sF2;
-        o.f1 = S[(d & ((1 << kUA0Bits) - 1)) + lane];
-        const double *wp = W + (((d >> kUW0Shift) & ((1 << kUW0Bits) - 1)) - kFPad) + ((d & kUNeg) ? -lane : lane);
+    __device__ __forceinline__ int2 unit_addr(int u) const { return ((const int2 *)(smem_raw + P.so.desc))[warp * (P.U + 2) + u]; }
+    __device__ __forceinline__ void load_operands(int2 ua, Operands &o) const {
+        const unsigned l8 = 8u * (unsigned)lane;
+        const unsigned aS = (unsigned)ua.x + l8;
+        const unsigned aW = ((unsigned)ua.y & ~7u) + ((ua.y & 1) ? 0u - l8 : l8);
+        o.f1 = *(const double *)(smem_raw + aS);
 #pragma unroll
-        for (int r = 0; r < kRB; r++) o.w[r] = wp[r];
+        for (int r = 0; r < kRB; r++) o.w[r] = *(const double *)(smem_raw + aW + 8 * r);
     }
-    __device__ __forceinline__ void unit(int d, const Operands &o, const double (&t)[kUV], double (&acc)[kUV], double *&sl) {
-        if (d & kUNewEntry) {
-            park(acc, sl);
+    __device__ __forceinline__ void park(double (&acc)[kUV], double *&sl) const {
 #pragma unroll
-            for (int v = 0; v < kUV; v++) acc[v] = 0.0;
-            sl += kUV * kLaneStride;
-        }
-        // rows of the block that do not exist (a trailing block of the CTA's range) are skipped: warp-uniform branches
-        const int nr = (d >> kURowsShift) & 3;
-        { const double f = o.f1 * o.w[0]; acc[0] = fma(t[0], f, acc[0]); acc[1] = fma(t[1], f, acc[1]); acc[2] = fma(t[2], f, acc[2]); }
-        if (nr >= 1) { const double f = o.f1 * o.w[1]; acc[3] = fma(t[3], f, acc[3]); acc[4] = fma(t[4], f, acc[4]); acc[5] = fma(t[5], f, acc[5]); }
-        if (nr >= 2) { const double f = o.f1 * o.w[2]; acc[6] = fma(t[6], f, acc[6]); acc[7] = fma(t[7], f, acc[7]); acc[8] = fma(t[8], f, acc[8]); }
-        if (nr >= 3) { const double f = o.f1 * o.w[3]; acc[9] = fma(t[9], f, acc[9]); acc[10] = fma(t[10], f, acc[10]); acc[11] = fma(t[11], f, acc[11]); }
+        for (int v = 0; v < kUV; v++) { sl[v * kLaneStride] = acc[v]; acc[v] = 0.0; }
+        sl += kUV * kLaneStride;
+    }
+    __device__ __forceinline__ void unit(int flags, const Operands &o, const double (&t)[kUV], double (&acc)[kUV], double *&sl) const {
+        if (flags & 2) park(acc, sl);
+        const double f0 = o.f1 * o.w[0], f1 = o.f1 * o.w[1], f2 = o.f1 * o.w[2], f3 = o.f1 * o.w[3];
+        acc[0] = fma(t[0], f0, acc[0]); acc[1] = fma(t[1], f0, acc[1]); acc[2] = fma(t[2], f0, acc[2]);
+        acc[3] = fma(t[3], f1, acc[3]); acc[4] = fma(t[4], f1, acc[4]); acc[5] = fma(t[5], f1, acc[5]);
+        acc[6] = fma(t[6], f2, acc[6]); acc[7] = fma(t[7], f2, acc[7]); acc[8] = fma(t[8], f2, acc[8]);
+        acc[9] = fma(t[9], f3, acc[9]); acc[10] = fma(t[10], f3, acc[10]); acc[11] = fma(t[11], f3, acc[11]);
     }
 
     // evaluate_kernel!(K, kernel, F, t) for the whole team (src/Kernels/ModeCouplingKernels.jl:211-228, 450-467),
@@ -221,58 +232,63 @@ struct Team {
             double acc[kUV];
 #pragma unroll
             for (int v = 0; v < kUV; v++) acc[v] = 0.0;
-            double *const sl0 = sLane + (size_t)warp * P.lane_cap * kUV * kLaneStride + (lane & 15);
-            double *sl = sl0;
-            const int US = P.US;
-            const int UG = kSlim ? 0 : P.U - UR - US;           // units that fit neither registers nor shared memory: from L2
+            double *const sl0 = sLane + (size_t)warp * P.lane_cap * kUV * kLaneStride;
+            double *sl = sl0 + lane;
+            const int UT = P.UT, US = P.US;             // units in tensor memory, in shared memory
+            const int UG = P.U - UR - UT - US;          // units that fit nowhere on chip: from L2
+            // software pipeline: op = operands of the current unit, fl = its flags, uan = addresses of the next unit
             Operands op, nop;
-            int dn = (UR > 0) ? udesc[0] : (US > 0 ? sDesc[warp * US] : (UG > 0 ? __ldg(P.udesc + slab_base + (long long)warp * P.U) : 0));
-            load_operands(dn, op);
-#ifdef MCT_PROFILE
-            if (!(P.dbg & 256))
-#endif
-#pragma unroll
-            for (int u = 0; u < UR; u++) {
-                const int d = dn;
-                dn = (u + 1 < UR) ? udesc[u + 1] : (US > 0 ? sDesc[warp * US] : (UG > 0 ? __ldg(P.udesc + slab_base + (long long)warp * P.U + UR) : 0));
-                load_operands(dn, nop);
-                unit(d, op, tab[u], acc, sl);
-                op = nop;
+            int2 uan = unit_addr(0);
+            load_operands(uan, op);
+            int fl = uan.y;
+            uan = unit_addr(1);
+            int u = 0;
+#define MCT_UNIT_STEP(TABLE)                                                  \
+            {                                                                     \
+                load_operands(uan, nop);                                          \
+                const int fln = uan.y;                                            \
+                uan = unit_addr(u + 2);                                           \
+                TABLE;                                                            \
+                unit(fl, op, t, acc, sl);                                         \
+                op = nop; fl = fln; u++;                                          \
             }
-#ifdef MCT_PROFILE
-            if (!(P.dbg & 512))
-#endif
-            for (int u = 0; u < US; u++) {
+#pragma unroll
+            for (int i = 0; i < UR; i++) {
+                const double (&t)[kUV] = tab[i];
+                MCT_UNIT_STEP((void)0)
+            }
+#pragma unroll 2
+            for (int i = 0; i < UT; i++) {
                 double t[kUV];
-                const double *ts = sTab + ((size_t)(warp * US + u) * kUV) * 32 + lane;
+                unsigned r[24];
+                tmem_ld24(tbase + kTmemUnitCols * i, r);
+                MCT_UNIT_STEP(tmem_wait_ld(); _Pragma("unroll") for (int v = 0; v < kUV; v++) t[v] = __hiloint2double((int)r[2 * v + 1], (int)r[2 * v]))
+            }
+#pragma unroll 2
+            for (int i = 0; i < US; i++) {
+                double t[kUV];
+                const double *ts = sTab + ((size_t)(warp * US + i) * kUV) * 32 + lane;
 #pragma unroll
                 for (int v = 0; v < kUV; v++) t[v] = ts[v * 32];
-                const int d = dn;
-                dn = (u + 1 < US) ? sDesc[warp * US + u + 1] : (UG > 0 ? __ldg(P.udesc + slab_base + (long long)warp * P.U + UR + US) : 0);
-                load_operands(dn, nop);
-                unit(d, op, t, acc, sl);
-                op = nop;
+                MCT_UNIT_STEP((void)0)
             }
-            for (int u = 0; u < UG; u++) {
-                const long long slot = slab_base + (long long)warp * P.U + UR + US + u;
+            for (int i = 0; i < UG; i++) {
+                const long long slot = slab_base + (long long)warp * P.U + UR + UT + US + i;
                 double t[kUV];
                 const double *ts = gtab + (slot * kUV) * 32 + lane;
 #pragma unroll
                 for (int v = 0; v < kUV; v++) t[v] = __ldg(ts + v * 32);
-                const int d = dn;
-                dn = (u + 1 < UG) ? __ldg(P.udesc + slot + 1) : 0;
-                load_operands(dn, nop);
-                unit(d, op, t, acc, sl);
-                op = nop;
+                MCT_UNIT_STEP((void)0)
             }
-            // last entry, then lanes add the 16 half-warp partials of the 12*we_n columns
+#undef MCT_UNIT_STEP
+            // last entry, then the lanes add the 32 lane partials of the 12*we_n columns
             if (we_n > 0) park(acc, sl);
             __syncwarp();
             for (int c = lane; c < kUV * we_n; c += 32) {
-                const double *col = sl0 - (lane & 15) + (size_t)c * kLaneStride;
+                const double *col = sl0 + (size_t)c * kLaneStride;
                 double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
-                for (int i = 0; i < 16; i += 4) { s0 += col[i]; s1 += col[i + 1]; s2 += col[i + 2]; s3 += col[i + 3]; }
+                for (int i = 0; i < 32; i += 4) { s0 += col[i]; s1 += col[i + 1]; s2 += col[i + 2]; s3 += col[i + 3]; }
                 sPart[we0 * kUV + c] = (s0 + s1) + (s2 + s3);
             }
         }
@@ -318,13 +334,13 @@ struct Team {
                                             double (&out)[KPT]) {
         PROF(3);
         unsigned long long w[KPT];
-        if (!kSlim && P.G == 1) {
+        if (P.G == 1) {
             if (tid < nrows) sX[tid] = v;
             __syncthreads();
 #pragma unroll
             for (int j = 0; j < KPT; j++) { const int k = j * kThreads + tid; w[j] = (k < P.Nk) ? (unsigned long long)__double_as_longlong(sX[k]) : 0ull; }
             PROF(5);
-        } else if (!kSlim && P.fabric == 1) {
+        } else if (P.fabric == 1) {
             // ---- cluster fabric: the team is one thread-block cluster; every CTA owns a copy of the exchange buffers in its
             //      shared memory and the publishers store straight into all of them (DSMEM).  Collecting is a local spin.
             epoch++;
@@ -422,6 +438,7 @@ struct Team {
                     const bool stop = again && spin_check(t0, spins);
                     if (!__any_sync(0xffffffffu, again) || __any_sync(0xffffffffu, stop)) break;
                 }
+                SNAP(24);
 #pragma unroll
                 for (int i = 0; i < kTotPieces; i++)
                     if (i * 32 + lane < np) { stg[2 * (i * 32 + lane)] = bits2d(pa[i]); stg[2 * (i * 32 + lane) + 1] = bits2d(pb[i]); }
@@ -442,6 +459,7 @@ struct Team {
 #pragma unroll
                 for (int i = 0; i < kTotPerLane; i++)
                     if (c0 + i < P.G) { sOff[c0 + i] = e1 + l1[i]; sOff[GP + c0 + i] = e2 + l2[i]; sOff[2 * GP + c0 + i] = e3 + l3[i]; }
+                SNAP(25);
             }
             while (true) {
                 bool again = false;
@@ -486,15 +504,41 @@ struct Team {
 
     // ------------------------------------------------------------------------------------------ per-equation setup
     __device__ __forceinline__ void load_tables(const EqDev &E) {
+        // operand addresses of this warp's units (see eval_rows); two dummy entries behind the last unit (prefetch)
+        for (int u = lane; u < P.U + 2; u += 32) {
+            int2 ua = make_int2((int)P.so.F2, (int)P.so.F2);
+            if (u < P.U) {
+                const int d = P.udesc[slab_base + (long long)warp * P.U + u];
+                const unsigned oS = (d & kUSwap) ? P.so.F2 : oF1, oW = (d & kUSwap) ? oF1 : P.so.F2;
+                ua.x = (int)(oS + 8u * (unsigned)(d & ((1 << kUA0Bits) - 1)));
+                ua.y = (int)(oW + 8u * (unsigned)(((d >> kUW0Shift) & ((1 << kUW0Bits) - 1))) - 8u * (unsigned)kFPad) | ((d & kUNeg) ? 1 : 0) | ((d & kUNewEntry) ? 2 : 0);
+            }
+            ((int2 *)(smem_raw + P.so.desc))[warp * (P.U + 2) + u] = ua;
+        }
+        __syncwarp();
 #pragma unroll
         for (int u = 0; u < UR; u++) {
             const long long slot = slab_base + (long long)warp * P.U + u;
 #pragma unroll
             for (int v = 0; v < kUV; v++) tab[u][v] = (u < P.U) ? __ldg(E.tab + (slot * kUV + v) * 32 + lane) : 0.0;
         }
-        const int US = P.US;
-        for (int u = 0; u < US; u++) {
+        const int UT = P.UT, US = P.US;
+        for (int u = 0; u < UT; u++) {
             const long long slot = slab_base + (long long)warp * P.U + UR + u;
+#pragma unroll
+            for (int h = 0; h < 3; h++) {
+                unsigned r[8];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const double x = __ldg(E.tab + (slot * kUV + 4 * h + i) * 32 + lane);
+                    r[2 * i] = (unsigned)__double2loint(x); r[2 * i + 1] = (unsigned)__double2hiint(x);
+                }
+                tmem_st8(tbase + kTmemUnitCols * u + 8 * h, r);
+            }
+        }
+        if (UT > 0) tmem_wait_st();
+        for (int u = 0; u < US; u++) {
+            const long long slot = slab_base + (long long)warp * P.U + UR + UT + u;
             for (int v = 0; v < kUV; v++) sTab[((size_t)(warp * US + u) * kUV + v) * 32 + lane] = __ldg(E.tab + (slot * kUV + v) * 32 + lane);
         }
     }
@@ -802,9 +846,6 @@ __global__ void __launch_bounds__(kThreads, 1) td_sc_kernel(const SolveParams P)
         T.eb1 = (T.tid < T.nrows) ? eb[T.tid / kRB + 1] : 0;
 #pragma unroll
         for (int j = 0; j < KPT; j++) { const int k = j * kThreads + T.tid; T.owner[j] = (k < P.Nk) ? P.row_owner[k] : 0; }
-#pragma unroll
-        for (int u = 0; u < UR; u++) T.udesc[u] = (u < P.U) ? P.udesc[T.slab_base + (long long)T.warp * P.U + u] : 0;
-        if (T.lane < P.US) ((int *)(smem_raw + P.so.desc))[T.warp * P.US + T.lane] = P.udesc[T.slab_base + (long long)T.warp * P.U + UR + T.lane];
         // zero padding around the F arrays (window operands of padding lanes)
         for (int i = T.tid; i < kFPad; i += kThreads) {
             double *f1 = (double *)(smem_raw + P.so.F1), *f2 = (double *)(smem_raw + P.so.F2);
@@ -816,6 +857,19 @@ __global__ void __launch_bounds__(kThreads, 1) td_sc_kernel(const SolveParams P)
         if (T.tid == 0) *(volatile int *)(smem_raw + P.so.misc) = 0;
         if (P.fabric == 1)
             for (int i = T.tid; i < 4 * P.xbuf_words; i += kThreads) ((unsigned long long *)(smem_raw + P.so.xd))[i] = kSentinel;
+    }
+    T.tbase = 0;
+    if (P.UT > 0) {
+        // the whole tensor memory of the SM for this CTA (one CTA per SM: 64 K registers); warp w: lanes 32 (w % 4), column half w / 4
+        unsigned *slot = (unsigned *)(smem_raw + P.so.misc) + 2;
+        if (T.warp == 0) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "n"(kTmemCols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        T.tbase = *(volatile unsigned *)slot + ((unsigned)(32 * (T.warp & 3)) << 16) + (unsigned)((T.warp >> 2) * (kTmemCols / 2));
     }
     __syncthreads();
     if (P.fabric == 1) cluster_sync_all();        // nobody stores into a peer before its buffers are armed
@@ -838,6 +892,11 @@ __global__ void __launch_bounds__(kThreads, 1) td_sc_kernel(const SolveParams P)
         __syncthreads();
     }
     if (P.fabric == 1) cluster_sync_all();        // a CTA must not exit while peers may still store into its shared memory
+    if (P.UT > 0) {
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (T.warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*(volatile unsigned *)((unsigned *)(smem_raw + P.so.misc) + 2)), "n"(kTmemCols) : "memory");
+    }
 #ifdef MCT_PROFILE
     if (team == 0 && T.tid == 0 && P.prof) {
         long long g_end;
