@@ -388,7 +388,7 @@ static int run_batch(int n, mct_equation_t *eqs, int mode, double tol, long long
     P.U = L->U; P.UR = res.UR; P.UT = res.UT; P.US = res.US; P.lane_cap = res.lane_cap;
     P.rows_max = L->rows_max; P.rb_max = L->rb_max; P.ent_max = L->ent_max;
     P.udesc = L->d_udesc; P.cta_meta = L->d_cta_meta; P.ent_begin = L->d_ent_begin; P.warp_ent = L->d_warp_ent; P.row_owner = L->d_row_owner;
-    P.xbuf_words = L->xbuf_words; P.fabric = fabric;
+    P.xbuf_words = L->xbuf_words; P.xrows = L->xrows; P.fabric = fabric;
     P.xstride = 4LL * L->xbuf_words + 16;      // four rotating buffers + the arrival counter (own line)
     P.poll_delay = env_int("MCT_POLL_DELAY", 300);
     P.poll_backoff = env_int("MCT_POLL_BACKOFF", 100);
@@ -450,7 +450,7 @@ static int run_batch(int n, mct_equation_t *eqs, int mode, double tol, long long
         std::vector<long long> pr((size_t)P.G * kProfSlots);
         cudaMemcpy(pr.data(), P.prof, pbytes, cudaMemcpyDeviceToHost);
         static const char *nm[kProfSlots] = {"stream+warp reduce", "barrier", "row sums+prefix", "F_loc", "publish+delay", "collect", "offset scan+barrier",
-                                            "apply+or-barrier", "between", "step-local", "=exchange alone", "=eval alone", "=eval+exchange", "-", "x:loads", "x:scan", "x:sync", "x:offsets", "x:or-barrier", "-", "-", "-", "-", "-", "-", "-", "-", "-", "-", "-", "TOTAL cycles", "TOTAL ns"};
+                                            "apply+or-barrier", "between", "step-local", "=exchange alone", "=eval alone", "=eval+exchange", "retries: totals", "retries: rows", "x:scan", "x:sync", "x:offsets", "x:or-barrier", "-", "-", "-", "-", "-", "-", "-", "-", "-", "-", "-", "TOTAL cycles", "TOTAL ns"};
         const int ctas[3] = {0, P.G / 2, P.G - 1};
         fprintf(stderr, "[mct profile] Nk=%d G=%d nteams=%d U=%d UR=%d UT=%d US=%d; thread 0 of CTA %d / %d / %d (team 0)\n", P.Nk, P.G, nteams,
                 P.U, P.UR, P.UT, P.US, ctas[0], ctas[1], ctas[2]);

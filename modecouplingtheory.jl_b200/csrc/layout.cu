@@ -234,7 +234,8 @@ int layout_build_geometry(TeamLayout &L, int Nk, int G, int sym) {
         L.ent_max = std::max(L.ent_max, n_ent);
         meta[4 * c] = r0; meta[4 * c + 1] = r1 - r0; meta[4 * c + 2] = n_ent;
     }
-    L.xbuf_words = 4 * G + ((Nk + 15) / 16) * 16 + 16;
+    L.xrows = std::max(4 * G, 3 * (((G + 15) / 16) * 16));     // totals: [G][4] (cluster fabric) or [3][G rounded to a line] (L2 fabric)
+    L.xbuf_words = L.xrows + ((Nk + 15) / 16) * 16 + 16;
     auto up = [](int **dst, const std::vector<int> &v) {
         cudaError_t e = cudaMalloc(dst, std::max<size_t>(1, v.size()) * sizeof(int));
         if (e == cudaSuccess) e = cudaMemcpy(*dst, v.data(), v.size() * sizeof(int), cudaMemcpyHostToDevice);

@@ -57,6 +57,7 @@ struct TeamLayout {
     int *d_warp_ent = nullptr;   // [G][9]: first entry of each warp
     int *d_row_owner = nullptr;  // [Nk]: owner CTA of each row
     int xbuf_words = 0;          // words (doubles) of one exchange buffer
+    int xrows = 0;               // offset of the rows inside an exchange buffer (the block totals come first)
     long long slab_doubles() const { return n_units * kUV * 32; }
 };
 

@@ -39,6 +39,7 @@ struct SolveParams {
     // team communication
     double *xbuf;               // [nteams][4][xbuf_words]: rotating exchange buffers of self-validating 8-byte slots
     int xbuf_words;
+    int xrows;                  // offset of the rows inside an exchange buffer (the block totals come first)
     int fabric;                 // 0: exchange through L2 (any team size); 1: the team is a thread-block cluster (G <= 16), DSMEM
     long long xstride;          // doubles per team: 4*xbuf_words + 16 (arrival counter)
     int poll_delay;             // ns between publishing and the first collecting load

@@ -29,7 +29,6 @@ namespace {
 
 constexpr unsigned long long kSentinel = 0xFFFFFFFFFFFFFFFFull;   // a NaN payload no arithmetic produces
 constexpr int kTotPerLane = 5;                                     // block totals per lane of the scanning warp -> G <= 160
-constexpr int kTotPieces = 10;                                     // 16-byte pieces of the totals [G][4] per lane (2G <= 320)
 
 
 extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -129,7 +128,8 @@ struct Team {
 #define RP (even_up(P.rows_max))
     int row0, nrows;             // rows owned by this CTA: [row0, row0 + nrows)
     int we0, we_n;               // first (warp,row) entry of this warp and how many it has
-    int eb0, eb1;                // owner thread tid < nrows: entries of its row
+    int eb0, eb1;                // entries of the row this thread adds up: row tid, or (3 rows_max <= 32) row prow of table pm
+    int prow, pm;
     int owner[KPT];              // owner CTA of the rows this thread finishes (k = j*kThreads + tid: consecutive lanes,
                                  // consecutive rows -- conflict-free in shared memory, coalesced in the exchange buffer)
     // register-resident part of the tables: the 12 values of this lane for the first UR units of the warp
@@ -296,14 +296,29 @@ struct Team {
         __syncthreads();
         PROF(1);
         // increments of the owned rows, inclusive prefix over them
-        double i1 = 0.0, i2 = 0.0, i3 = 0.0;
-        if (tid < nrows) {
-            const int r3 = 3 * (tid & (kRB - 1));          // row inside its row block
-            for (int e = eb0; e < eb1; e++) { i1 += sPart[e * kUV + r3]; i2 += sPart[e * kUV + r3 + 1]; i3 += sPart[e * kUV + r3 + 2]; }
+        if (3 * P.rows_max <= 32) {
+            // warp 0, lane (m, r) = (table, row): the three prefixes run side by side in one segmented scan; the owner thread of
+            // row r then fetches its three sums.  Same additions in the same order as the scan of three values per lane.
+            L1 = L2 = L3 = 0.0;
+            if (warp == 0) {
+                const int RM = P.rows_max;
+                double x = 0.0;
+                const int c3 = 3 * (prow & (kRB - 1)) + pm;
+                for (int e = eb0; e < eb1; e++) x += sPart[e * kUV + c3];
+                for (int o = 1; o < RM; o <<= 1) { const double up = __shfl_up_sync(0xffffffffu, x, o); if (prow >= o) x += up; }
+                const int sl = (lane < RM) ? lane : 0;
+                L1 = __shfl_sync(0xffffffffu, x, sl); L2 = __shfl_sync(0xffffffffu, x, RM + sl); L3 = __shfl_sync(0xffffffffu, x, 2 * RM + sl);
+            }
+        } else {
+            double i1 = 0.0, i2 = 0.0, i3 = 0.0;
+            if (tid < nrows) {
+                const int r3 = 3 * (tid & (kRB - 1));          // row inside its row block
+                for (int e = eb0; e < eb1; e++) { i1 += sPart[e * kUV + r3]; i2 += sPart[e * kUV + r3 + 1]; i3 += sPart[e * kUV + r3 + 2]; }
+            }
+            if (P.rows_max <= 32) { if (warp == 0) warp_inscan3(i1, i2, i3); }
+            else block_inscan3(i1, i2, i3);
+            L1 = i1; L2 = i2; L3 = i3;
         }
-        if (P.rows_max <= 32) { if (warp == 0) warp_inscan3(i1, i2, i3); }
-        else block_inscan3(i1, i2, i3);
-        L1 = i1; L2 = i2; L3 = i3;
         PROF(2);
 #ifdef MCT_PROFILE
         if (epoch + 1 == (unsigned)P.snap_epoch) { long long g__; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g__)); prof[25] = g__; }
@@ -347,9 +362,9 @@ struct Team {
             double *lcur = sXD + (size_t)(epoch & 3u) * P.xbuf_words, *lclr = sXD + (size_t)((epoch + 2u) & 3u) * P.xbuf_words;
             // re-arm the own copy of the buffer used two exchanges from now (peers write it only after they have seen this
             // CTA's data of the next exchange, which is published after the barrier that ends this one)
-            for (int i = tid; i < 4 * P.G + P.Nk; i += kThreads) ((unsigned long long *)lclr)[i] = kSentinel;
+            for (int i = tid; i < P.xrows + P.Nk; i += kThreads) ((unsigned long long *)lclr)[i] = kSentinel;
             if (tid < nrows) {
-                const unsigned a = smem_u32(lcur + 4 * P.G + row0 + tid);
+                const unsigned a = smem_u32(lcur + P.xrows + row0 + tid);
                 for (int p = 0; p < P.G; p++) st_cluster(a, p, v);
             }
             if (tid == nrows - 1) {
@@ -373,7 +388,7 @@ struct Team {
             for (int j = 0; j < KPT; j++) {
                 const int k = j * kThreads + tid;
                 w[j] = 0;
-                if (k < P.Nk) { while ((w[j] = ld_smem_relaxed_bits(lcur + 4 * P.G + k)) == kSentinel) { if (spin_check(t0, spins)) break; } }
+                if (k < P.Nk) { while ((w[j] = ld_smem_relaxed_bits(lcur + P.xrows + k)) == kSentinel) { if (spin_check(t0, spins)) break; } }
             }
             PROF(5);
             if (warp == 0) {     // G <= 16: one warp scans the totals
@@ -397,10 +412,11 @@ struct Team {
 #define SNAP(i) do { } while (0)
 #endif
             SNAP(19);
-            if (tid < nrows) st_relaxed(cur + 4 * P.G + row0 + tid, v);
-            if (tid == nrows - 1) { st_relaxed2(cur + 4 * cta, B1, B2); st_relaxed2(cur + 4 * cta + 2, B3, 0.0); }
-            if (tid < nrows) st_relaxed_bits(clr + 4 * P.G + row0 + tid, kSentinel);
-            if (tid == nrows - 1) { st_relaxed2_bits(clr + 4 * cta, kSentinel, kSentinel); st_relaxed2_bits(clr + 4 * cta + 2, kSentinel, kSentinel); }
+            const int GT = (P.G + 15) & ~15;                 // block totals: three arrays [GT], one per vertex table
+            if (tid < nrows) st_relaxed(cur + P.xrows + row0 + tid, v);
+            if (tid == nrows - 1) { st_relaxed(cur + cta, B1); st_relaxed(cur + GT + cta, B2); st_relaxed(cur + 2 * GT + cta, B3); }
+            if (tid < nrows) st_relaxed_bits(clr + P.xrows + row0 + tid, kSentinel);
+            if (tid == nrows - 1) { st_relaxed_bits(clr + cta, kSentinel); st_relaxed_bits(clr + GT + cta, kSentinel); st_relaxed_bits(clr + 2 * GT + cta, kSentinel); }
             const long long t0 = clock64();
             unsigned spins = 0;
             PROF(4);
@@ -419,46 +435,40 @@ struct Team {
             SNAP(20);
             PROF(5);
             // one shot: the rows of every thread; re-issue only what still shows the sentinel
-            const double *src = cur + 4 * P.G + tid;
+            const double *src = cur + P.xrows + tid;
 #pragma unroll
             for (int j = 0; j < KPT; j++) { w[j] = 0ull; if (j * kThreads + tid < P.Nk) w[j] = ld_relaxed_bits(src + j * kThreads); }
-            if (warp == 0) {
-                // block totals [G][4] in 16-byte pieces, coalesced; staged in the (idle) warp scratch so that lane l gets the
-                // kTotPerLane consecutive CTAs it scans
-                double *stg = sLane;
-                const int np = 2 * P.G;
-                unsigned long long pa[kTotPieces], pb[kTotPieces];
+            if (warp < 3) {
+                // warp m scans the block totals of table m while the rows are in flight: coalesced loads (lane l: CTAs l + 32 i),
+                // transposed through the idle warp scratch so that lane l holds the kTotPerLane consecutive CTAs it adds
+                // serially, one warp scan of the lane sums; exclusive prefix in a fixed order, identical in every CTA
+                const double *tp = cur + warp * GT;
+                double *stg = sLane + warp * (32 * kTotPerLane);
+                unsigned long long tv[kTotPerLane];
 #pragma unroll
-                for (int i = 0; i < kTotPieces; i++) { pa[i] = pb[i] = 0ull; if (i * 32 + lane < np) ld_relaxed2_bits(cur + 2 * (i * 32 + lane), pa[i], pb[i]); }
+                for (int i = 0; i < kTotPerLane; i++) { tv[i] = 0ull; if (i * 32 + lane < P.G) tv[i] = ld_relaxed_bits(tp + i * 32 + lane); }
                 while (true) {
                     bool again = false;
 #pragma unroll
-                    for (int i = 0; i < kTotPieces; i++)
-                        if (pa[i] == kSentinel || pb[i] == kSentinel) { ld_relaxed2_bits(cur + 2 * (i * 32 + lane), pa[i], pb[i]); again = true; }
+                    for (int i = 0; i < kTotPerLane; i++)
+                        if (tv[i] == kSentinel) { tv[i] = ld_relaxed_bits(tp + i * 32 + lane); again = true; }
                     const bool stop = again && spin_check(t0, spins);
                     if (!__any_sync(0xffffffffu, again) || __any_sync(0xffffffffu, stop)) break;
                 }
                 SNAP(24);
 #pragma unroll
-                for (int i = 0; i < kTotPieces; i++)
-                    if (i * 32 + lane < np) { stg[2 * (i * 32 + lane)] = bits2d(pa[i]); stg[2 * (i * 32 + lane) + 1] = bits2d(pb[i]); }
+                for (int i = 0; i < kTotPerLane; i++) stg[i * 32 + lane] = bits2d(tv[i]);
                 __syncwarp();
-                // exclusive prefix of the G block totals in a fixed order (identical in every CTA): serial inside a lane,
-                // warp scan of the lane sums
-                double l1[kTotPerLane], l2[kTotPerLane], l3[kTotPerLane];
-                double s1 = 0.0, s2 = 0.0, s3 = 0.0;
-                const int c0 = lane * kTotPerLane;
+                double le[kTotPerLane], s = 0.0;
 #pragma unroll
-                for (int i = 0; i < kTotPerLane; i++) {
-                    l1[i] = s1; l2[i] = s2; l3[i] = s3;
-                    if (c0 + i < P.G) { s1 += stg[4 * (c0 + i)]; s2 += stg[4 * (c0 + i) + 1]; s3 += stg[4 * (c0 + i) + 2]; }
-                }
-                double e1 = s1, e2 = s2, e3 = s3;
-                warp_inscan3(e1, e2, e3);
-                e1 -= s1; e2 -= s2; e3 -= s3;
+                for (int i = 0; i < kTotPerLane; i++) { le[i] = s; s += stg[kTotPerLane * lane + i]; }
+                double e = s;
 #pragma unroll
-                for (int i = 0; i < kTotPerLane; i++)
-                    if (c0 + i < P.G) { sOff[c0 + i] = e1 + l1[i]; sOff[GP + c0 + i] = e2 + l2[i]; sOff[2 * GP + c0 + i] = e3 + l3[i]; }
+                for (int o = 1; o < 32; o <<= 1) { const double up = __shfl_up_sync(0xffffffffu, e, o); if (lane >= o) e += up; }
+                e -= s;
+                double *so = sOff + warp * GP + kTotPerLane * lane;
+#pragma unroll
+                for (int i = 0; i < kTotPerLane; i++) if (kTotPerLane * lane + i < P.G) so[i] = e + le[i];
                 SNAP(25);
             }
             while (true) {
@@ -466,6 +476,9 @@ struct Team {
 #pragma unroll
                 for (int j = 0; j < KPT; j++)
                     if (w[j] == kSentinel) { w[j] = ld_relaxed_bits(src + j * kThreads); again = true; }
+#ifdef MCT_PROFILE
+                if (again) prof[14]++;
+#endif
                 if (!again || spin_check(t0, spins)) break;
             }
             SNAP(21);
@@ -842,8 +855,12 @@ __global__ void __launch_bounds__(kThreads, 1) td_sc_kernel(const SolveParams P)
         T.we0 = P.warp_ent[T.cta * (kWarps + 1) + T.warp];
         T.we_n = P.warp_ent[T.cta * (kWarps + 1) + T.warp + 1] - T.we0;
         const int *eb = P.ent_begin + (size_t)T.cta * (P.rb_max + 1);
-        T.eb0 = (T.tid < T.nrows) ? eb[T.tid / kRB] : 0;
-        T.eb1 = (T.tid < T.nrows) ? eb[T.tid / kRB + 1] : 0;
+        const bool split = 3 * P.rows_max <= 32;
+        T.pm = split ? min(T.tid / P.rows_max, 2) : 0;
+        T.prow = split ? T.tid % P.rows_max : T.tid;
+        const bool sums = T.prow < T.nrows && (!split || T.tid < 3 * P.rows_max);
+        T.eb0 = sums ? eb[T.prow / kRB] : 0;
+        T.eb1 = sums ? eb[T.prow / kRB + 1] : 0;
 #pragma unroll
         for (int j = 0; j < KPT; j++) { const int k = j * kThreads + T.tid; T.owner[j] = (k < P.Nk) ? P.row_owner[k] : 0; }
         // zero padding around the F arrays (window operands of padding lanes)
