@@ -390,8 +390,6 @@ static int run_batch(int n, mct_equation_t *eqs, int mode, double tol, long long
     P.udesc = L->d_udesc; P.cta_meta = L->d_cta_meta; P.ent_begin = L->d_ent_begin; P.warp_ent = L->d_warp_ent; P.row_owner = L->d_row_owner;
     P.xbuf_words = L->xbuf_words; P.xrows = L->xrows; P.fabric = fabric;
     P.xstride = 4LL * L->xbuf_words + 16;      // four rotating buffers + the arrival counter (own line)
-    P.poll_delay = env_int("MCT_POLL_DELAY", 300);
-    P.poll_backoff = env_int("MCT_POLL_BACKOFF", 100);
     P.dbg = env_int("MCT_DBG", 0);
     P.snap_epoch = env_int("MCT_SNAP_EPOCH", 1000);
     P.spin_limit_cycles = (long long)env_int("MCT_SPIN_LIMIT_MS", 2000) * 2000000LL;
@@ -449,8 +447,20 @@ static int run_batch(int n, mct_equation_t *eqs, int mode, double tol, long long
     {
         std::vector<long long> pr((size_t)P.G * kProfSlots);
         cudaMemcpy(pr.data(), P.prof, pbytes, cudaMemcpyDeviceToHost);
+        if (getenv("MCT_DUMP_CTAS")) {
+            fprintf(stderr, "per CTA (thread 0), kilo-cycles: cta rows | units+reduce  row-sums  publish  collect(wait)  loads+scan  apply  step-local\n");
+            for (int c = 0; c < P.G; c++) {
+                const long long *q = &pr[(size_t)c * kProfSlots];
+                fprintf(stderr, "  %3d | %8lld %8lld %8lld %8lld %8lld %8lld %8lld\n", c, q[0] / 1000, q[2] / 1000, q[4] / 1000, q[5] / 1000, q[6] / 1000, q[7] / 1000, q[9] / 1000);
+            }
+        }
+        if (getenv("MCT_DUMP_BEACON")) {
+            fprintf(stderr, "beacons (cta:epoch.phase):");
+            for (int c = 0; c < P.G; c++) fprintf(stderr, " %d:%lld.%lld", c, pr[(size_t)c * kProfSlots + 28] / 16, pr[(size_t)c * kProfSlots + 28] % 16);
+            fprintf(stderr, "\n");
+        }
         static const char *nm[kProfSlots] = {"stream+warp reduce", "barrier", "row sums+prefix", "F_loc", "publish+delay", "collect", "offset scan+barrier",
-                                            "apply+or-barrier", "between", "step-local", "=exchange alone", "=eval alone", "=eval+exchange", "retries: totals", "retries: rows", "x:scan", "x:sync", "x:offsets", "x:or-barrier", "-", "-", "-", "-", "-", "-", "-", "-", "-", "-", "-", "TOTAL cycles", "TOTAL ns"};
+                                            "apply+or-barrier", "between", "step-local", "=exchange alone", "=eval alone", "=eval+exchange", "-", "retries: rows", "-", "-", "x:offsets", "x:or-barrier", "-", "-", "-", "-", "-", "-", "-", "-", "-", "-", "-", "TOTAL cycles", "TOTAL ns"};
         const int ctas[3] = {0, P.G / 2, P.G - 1};
         fprintf(stderr, "[mct profile] Nk=%d G=%d nteams=%d U=%d UR=%d UT=%d US=%d; thread 0 of CTA %d / %d / %d (team 0)\n", P.Nk, P.G, nteams,
                 P.U, P.UR, P.UT, P.US, ctas[0], ctas[1], ctas[2]);

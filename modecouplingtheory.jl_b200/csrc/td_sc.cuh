@@ -42,8 +42,6 @@ struct SolveParams {
     int xrows;                  // offset of the rows inside an exchange buffer (the block totals come first)
     int fabric;                 // 0: exchange through L2 (any team size); 1: the team is a thread-block cluster (G <= 16), DSMEM
     long long xstride;          // doubles per team: 4*xbuf_words + 16 (arrival counter)
-    int poll_delay;             // ns between publishing and the first collecting load
-    int poll_backoff;           // ns between two collecting attempts
     int *queue;                 // next equation to solve
     double *qbox;               // [nteams][4*16]: rotating mailbox for the equation index
     int *abort_flag;

@@ -98,6 +98,11 @@ constexpr int kTmemUnitCols = 2 * kUV;            // 24 columns of 32 bits = 12 
 #define PROF(i) do { } while (0)
 #endif
 
+#ifdef MCT_PROFILE
+#define BEACON(ph) do { if ((P.dbg & 2) && tid == 0 && P.prof && !*sAbort && !*(volatile int *)P.abort_flag) ((volatile long long *)P.prof)[((size_t)blockIdx.x) * kProfSlots + 28] = (long long)epoch * 16 + (ph); } while (0)
+#else
+#define BEACON(ph) do { } while (0)
+#endif
 enum { X_USE_OFF = 1, X_TRACK = 2 };
 
 template <int KPT, int UR>
@@ -162,7 +167,12 @@ struct Team {
     __device__ __forceinline__ bool spin_check(long long t0, unsigned &spins) {
         if ((++spins & 255u) == 0) {
             if (*(volatile int *)P.abort_flag) { *sAbort = 1; return true; }
-            if (clock64() - t0 > P.spin_limit_cycles) { atomicExch(P.abort_flag, 1); *sAbort = 1; return true; }
+            if (clock64() - t0 > P.spin_limit_cycles) {
+#ifdef MCT_PROFILE
+                if (atomicAdd(P.abort_flag + 1, 1) < 40) printf("[mct] spin timeout: cta %d tid %d epoch %u spins %u\n", cta, tid, epoch, spins);
+#endif
+                atomicExch(P.abort_flag, 1); *sAbort = 1; return true;
+            }
         }
         return false;
     }
@@ -225,6 +235,7 @@ struct Team {
     // tid < nrows: L_m = sum of the increments of rows row0 .. row0+tid  (so T_m[k] = off_m(cta) + L_m).
     __device__ __forceinline__ void eval_rows(const double *__restrict__ gtab, double &L1, double &L2, double &L3) {
         PROF(8);
+        BEACON(7);
 #ifdef MCT_PROFILE
         if (epoch + 1 == (unsigned)P.snap_epoch) { long long g__; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g__)); prof[24] = g__; }
 #endif
@@ -293,8 +304,10 @@ struct Team {
             }
         }
         PROF(0);
+        BEACON(8);
         __syncthreads();
         PROF(1);
+        BEACON(9);
         // increments of the owned rows, inclusive prefix over them
         if (3 * P.rows_max <= 32) {
             // warp 0, lane (m, r) = (table, row): the three prefixes run side by side in one segmented scan; the owner thread of
@@ -412,6 +425,7 @@ struct Team {
 #define SNAP(i) do { } while (0)
 #endif
             SNAP(19);
+            BEACON(1);
             const int GT = (P.G + 15) & ~15;                 // block totals: three arrays [GT], one per vertex table
             if (tid < nrows) st_relaxed(cur + P.xrows + row0 + tid, v);
             if (tid == nrows - 1) { st_relaxed(cur + cta, B1); st_relaxed(cur + GT + cta, B2); st_relaxed(cur + 2 * GT + cta, B3); }
@@ -420,7 +434,10 @@ struct Team {
             const long long t0 = clock64();
             unsigned spins = 0;
             PROF(4);
-            // The counter is only a hint: no fence orders it after the data, the words still validate themselves.
+            BEACON(2);
+            // arrival counter: only a hint, no fence orders it after the data, the words still validate themselves.  (Timed arrival
+            // without any signal -- wait an adaptive delay after the own publish, load once, re-issue sentinels -- was built and
+            // measured in round 2: same speed, the wait is the arrival skew of the slowest CTA, not the counter's latency.)
             if (warp == 0) {
                 __syncwarp();
                 if (lane == 0) {
@@ -434,6 +451,7 @@ struct Team {
             asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory");
             SNAP(20);
             PROF(5);
+            BEACON(3);
             // one shot: the rows of every thread; re-issue only what still shows the sentinel
             const double *src = cur + P.xrows + tid;
 #pragma unroll
@@ -476,13 +494,12 @@ struct Team {
 #pragma unroll
                 for (int j = 0; j < KPT; j++)
                     if (w[j] == kSentinel) { w[j] = ld_relaxed_bits(src + j * kThreads); again = true; }
-#ifdef MCT_PROFILE
-                if (again) prof[14]++;
-#endif
                 if (!again || spin_check(t0, spins)) break;
             }
             SNAP(21);
+            BEACON(4);
             __syncthreads();
+            BEACON(5);
         }
         PROF(6);
         SNAP(22);
@@ -512,6 +529,7 @@ struct Team {
         const int any = __syncthreads_or(pred);
         PROF(7);
         SNAP(23);
+        BEACON(6);
         return any;
     }
 
@@ -724,6 +742,7 @@ struct Team {
             for (int it = n2 + 1; it <= n4 && status == MCT_OK; it++) {
                 const int i2 = it / 2;
                 const long long row = 1 + (long long)n2 * (blk + 1) + (it - n2 - 1);
+                BEACON(10);
                 // update_Fuchs_parameters! :300-319 for the owned wavenumbers: one warp per row, lanes over the history
                 for (int r = warp; r < nrows; r += kWarps) {
                     const int kr = row0 + r;
@@ -733,7 +752,9 @@ struct Team {
                     s1 = warp_sum(s1); s2 = warp_sum(s2);
                     if (lane == 0) { sC[r] = s1; sC[even_up(P.rows_max) + r] = s2; }
                 }
+                BEACON(11);
                 __syncthreads();
+                BEACON(12);
                 double Fc3 = 0.0, Finit = 0.0;
                 if (k >= 0) {
                     const double al = own(OWN_AL), be = own(OWN_BE), de_k = own(OWN_DE);
@@ -754,6 +775,7 @@ struct Team {
                 }
                 load_F1(E, row);
                 PROF(9);
+                BEACON(13);
                 exchange(Finit, 0.0, 0.0, 0.0, 0, fold, sF2, out);
                 // fixed-point loop :404-417
                 long long iter = 0;
@@ -769,6 +791,7 @@ struct Team {
                     if (!any) break;
                 }
                 if (status != MCT_OK) break;
+                BEACON(14);
                 // store the step + update_integrals! :377-384, allocate_results! :429-438 (owners)
                 if (k >= 0) {
                     const double Fn = sF2[k], K = K_exact(L1, L2, L3);
@@ -779,8 +802,10 @@ struct Team {
                 }
                 __syncthreads();
                 PROF(9);
+                BEACON(15);
             }
             if (status != MCT_OK) break;
+            BEACON(16);
             // new_time_mapping! :448-489 (owners, one warp per row; read everything of a chunk before writing it)
             for (int r = warp; r < nrows; r += kWarps) {
                 const int kr = row0 + r;
@@ -799,8 +824,11 @@ struct Team {
                 }
                 for (int j = n2 + 1 + lane; j <= n4; j += 32) { RING(FI, kr, j) = 0.0; RING(KI, kr, j) = 0.0; RING(Ft, kr, j) = 0.0; RING(Kt, kr, j) = 0.0; }
             }
+            BEACON(17);
             __syncthreads();
+            BEACON(18);
         }
+        BEACON(19);
         if (cta == 0 && tid == 0) { *E.status = status; *E.kernel_evals = evals; }
 #undef RING
     }
@@ -920,7 +948,7 @@ __global__ void __launch_bounds__(kThreads, 1) td_sc_kernel(const SolveParams P)
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g_end));
         T.prof[kProfSlots - 2] = clock64() - t_begin;
         T.prof[kProfSlots - 1] = g_end - g_begin;
-        for (int i = 0; i < kProfSlots; i++) P.prof[T.cta * kProfSlots + i] = T.prof[i];
+        for (int i = 0; i < kProfSlots; i++) if (i != 28) P.prof[T.cta * kProfSlots + i] = T.prof[i];
     }
 #endif
 }
