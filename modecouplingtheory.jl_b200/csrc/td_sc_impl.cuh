@@ -145,6 +145,7 @@ struct Team {
     double myoff1, myoff2, myoff3;   // offsets of this CTA from the last exchange
     long long slab_base;         // first slot of this CTA in the team layout
     unsigned tbase;              // tensor-memory address of this warp's first table unit
+    unsigned sbase;              // shared-space address of smem_raw
 #ifdef MCT_PROFILE
     long long prof[kProfSlots], tlast;
 #endif
@@ -356,9 +357,9 @@ struct Team {
     // totals (B1,B2,B3).  Every thread collects the rows k = j*kThreads + tid, every CTA scans the totals into sOff.
     //   X_USE_OFF: out = v_k - (rho_1[k] off_1 + rho_2[k] off_2 + rho_3[k] off_3) with the offsets of k's owner
     //   X_TRACK:   compare with fold (find_error, src/HelperFunctions.jl:55-64; F_old .= F, TimeDoublingSolver.jl:414)
-    //   dst:       shared array receiving out (or nullptr)
+    //   dst_off:   byte offset (in the dynamic shared memory) of the array receiving out, or -1
     // Returns non-zero iff some |out - fold| > tol (identical in every thread of every CTA).  Ends with a barrier.
-    __device__ __forceinline__ int exchange(double v, double B1, double B2, double B3, int flags, double (&fold)[KPT], double *dst,
+    __device__ __forceinline__ int exchange(double v, double B1, double B2, double B3, int flags, double (&fold)[KPT], int dst_off,
                                             double (&out)[KPT]) {
         PROF(3);
         unsigned long long w[KPT];
@@ -504,26 +505,26 @@ struct Team {
         PROF(6);
         SNAP(22);
         cta_offsets(cta, myoff1, myoff2, myoff3);
+        // finish the rows of this thread: branch-free (rows beyond Nk are computed on clamped addresses and discarded), all
+        // shared-memory loads first, so that the KPT rows overlap instead of running one after the other
         int pred = 0;
+        double o1[KPT], o2[KPT], o3[KPT], r1[KPT], r2[KPT], r3[KPT];
+        if (flags & X_USE_OFF) {
+#pragma unroll
+            for (int j = 0; j < KPT; j++) {
+                const int kc = min(j * kThreads + tid, P.Nk - 1);
+                cta_offsets(owner[j], o1[j], o2[j], o3[j]);
+                r1[j] = sRho[kc]; r2[j] = sRho[NkP + kc]; r3[j] = sRho[2 * NkP + kc];
+            }
+        }
 #pragma unroll
         for (int j = 0; j < KPT; j++) {
             const int k = j * kThreads + tid;
+            const bool valid = k < P.Nk;
             double f = bits2d(w[j]);
-            if (k < P.Nk) {
-#ifdef MCT_PROFILE
-                if ((flags & X_USE_OFF) && !(P.dbg & 64)) {
-                    double o1, o2, o3;
-                    if (P.dbg & 32) { o1 = myoff1; o2 = myoff2; o3 = myoff3; } else cta_offsets(owner[j], o1, o2, o3);
-#else
-                if (flags & X_USE_OFF) {
-                    double o1, o2, o3;
-                    cta_offsets(owner[j], o1, o2, o3);
-#endif
-                    f = f - (sRho[k] * o1 + sRho[NkP + k] * o2 + sRho[2 * NkP + k] * o3);
-                }
-                if (flags & X_TRACK) { pred |= (fabs(f - fold[j]) > P.tol) ? 1 : 0; fold[j] = f; }
-                if (dst) dst[k] = f;
-            }
+            if (flags & X_USE_OFF) { const double g = f - (r1[j] * o1[j] + r2[j] * o2[j] + r3[j] * o3[j]); f = valid ? g : f; }
+            if (flags & X_TRACK) { pred |= (valid && fabs(f - fold[j]) > P.tol) ? 1 : 0; fold[j] = f; }
+            if (dst_off >= 0 && valid) asm volatile("st.shared.f64 [%0], %1;" ::"r"(sbase + (unsigned)dst_off + 8u * (unsigned)k), "d"(f) : "memory");
             out[j] = f;
         }
         const int any = __syncthreads_or(pred);
@@ -599,7 +600,7 @@ struct Team {
         __syncthreads();
         double L1, L2, L3;
         eval_rows(E.tab, L1, L2, L3);                          // K = evaluate_kernel(kernel, F0, t) :66
-        exchange(f0, L1, L2, L3, 0, fold, nullptr, out);
+        exchange(f0, L1, L2, L3, 0, fold, -1, out);
         double K = K_exact(L1, L2, L3), Fn = f0;
         long long iter = 0;
         int status = MCT_OK;
@@ -607,9 +608,9 @@ struct Team {
             iter++;
             if (iter > P.max_iter) { status = MCT_NOT_CONVERGED; break; }   // :75-78
             Fn = (K * f0) / (K + g);                           // :81-84
-            const int any = exchange(Fn, 0.0, 0.0, 0.0, X_TRACK, fold, sF2, out);   // find_error(F, Fold); Fold .= F  :90-91
+            const int any = exchange(Fn, 0.0, 0.0, 0.0, X_TRACK, fold, (int)P.so.F2, out);   // find_error(F, Fold); Fold .= F  :90-91
             eval_rows(E.tab, L1, L2, L3);                      // :89 (the error does not depend on it)
-            exchange(Fn, L1, L2, L3, 0, fold, nullptr, out);
+            exchange(Fn, L1, L2, L3, 0, fold, -1, out);
             K = K_exact(L1, L2, L3);
             if (aborted()) { status = MCT_CUDA_ERROR; break; }
             if (!any) break;
@@ -633,15 +634,15 @@ struct Team {
         load_F1(E, 0);
         __syncthreads();
         eval_rows(E.tab, L1, L2, L3);
-        exchange(0.0, L1, L2, L3, 0, fold, nullptr, out);
+        exchange(0.0, L1, L2, L3, 0, fold, -1, out);
 #ifdef MCT_PROFILE
         {   // isolated cost of the two building blocks (cycles of thread 0, 2000 repetitions each)
             long long c0 = clock64();
-            for (int i = 0; i < 2000; i++) exchange(1.0 + i, 0.0, 0.0, 0.0, 0, fold, nullptr, out);
+            for (int i = 0; i < 2000; i++) exchange(1.0 + i, 0.0, 0.0, 0.0, 0, fold, -1, out);
             long long c1 = clock64();
             for (int i = 0; i < 2000; i++) { double l1, l2, l3; eval_rows(E.tab, l1, l2, l3); __syncthreads(); }
             long long c2 = clock64();
-            for (int i = 0; i < 2000; i++) { double l1, l2, l3; eval_rows(E.tab, l1, l2, l3); exchange(l1, l1, l2, l3, X_USE_OFF | X_TRACK, fold, nullptr, out); }
+            for (int i = 0; i < 2000; i++) { double l1, l2, l3; eval_rows(E.tab, l1, l2, l3); exchange(l1, l1, l2, l3, X_USE_OFF | X_TRACK, fold, -1, out); }
             long long c3 = clock64();
             prof[10] = (c1 - c0) / 2000; prof[11] = (c2 - c1) / 2000; prof[12] = (c3 - c2) / 2000;
             tlast = clock64();
@@ -651,7 +652,7 @@ struct Team {
             const double K0 = K_exact(L1, L2, L3), f0 = own(OWN_F0);
             if (k >= 0) { sOwn[OWN_K0 * RP + tid] = K0; E.F_out[k] = f0; E.K_out[k] = K0; }     // output row 0 (t = 0)
             // F_old = K0*F0 (:64) for every wavenumber
-            exchange(K0 * f0, 0.0, 0.0, 0.0, 0, fold, nullptr, out);
+            exchange(K0 * f0, 0.0, 0.0, 0.0, 0, fold, -1, out);
         }
 #pragma unroll
         for (int j = 0; j < KPT; j++) fold[j] = out[j];
@@ -691,9 +692,9 @@ struct Team {
                 RING(FI, k, it + 1) = dFn;
             }
             load_F1(E, it);
-            exchange(Fn, 0.0, 0.0, 0.0, 0, fold, sF2, out);
+            exchange(Fn, 0.0, 0.0, 0.0, 0, fold, (int)P.so.F2, out);
             eval_rows(E.tab, L1, L2, L3);
-            exchange(Fn, L1, L2, L3, 0, fold, nullptr, out);
+            exchange(Fn, L1, L2, L3, 0, fold, -1, out);
             if (k >= 0) {
                 const double K = K_exact(L1, L2, L3);
                 RING(Kt, k, it) = K;                           // == initialize_K_temp! :155-166
@@ -729,7 +730,7 @@ struct Team {
                 c1 = ((2.0 / (dl * dl) * own(OWN_AL) + 3.0 / (2.0 * dl) * own(OWN_BE)) + RING(KI, k, 1)) + own(OWN_GA);    // :314
                 c2 = RING(FI, k, 1) - own(OWN_F0);                                              // :315
             }
-            exchange(c2 / c1, 0.0, 0.0, 0.0, 0, fold, nullptr, out);
+            exchange(c2 / c1, 0.0, 0.0, 0.0, 0, fold, -1, out);
 #pragma unroll
             for (int j = 0; j < KPT; j++) {
                 const int kk = j * kThreads + tid;
@@ -776,7 +777,7 @@ struct Team {
                 load_F1(E, row);
                 PROF(9);
                 BEACON(13);
-                exchange(Finit, 0.0, 0.0, 0.0, 0, fold, sF2, out);
+                exchange(Finit, 0.0, 0.0, 0.0, 0, fold, (int)P.so.F2, out);
                 // fixed-point loop :404-417
                 long long iter = 0;
                 while (true) {
@@ -785,7 +786,7 @@ struct Team {
                     eval_rows(E.tab, L1, L2, L3);                                               // update_K! :360-369
                     const int kc = (k >= 0) ? k : 0;
                     const double Floc = Fc3 - (sRho[kc] * L1 + sRho[NkP + kc] * L2 + sRho[2 * NkP + kc] * L3);   // update_F! :333-336, CTA-local part
-                    const int any = exchange(Floc, L1, L2, L3, X_USE_OFF | X_TRACK, fold, sF2, out);   // find_error + F_old .= F
+                    const int any = exchange(Floc, L1, L2, L3, X_USE_OFF | X_TRACK, fold, (int)P.so.F2, out);   // find_error + F_old .= F
                     evals++;                                                                    // :416
                     if (aborted()) { status = MCT_CUDA_ERROR; break; }
                     if (!any) break;
@@ -866,6 +867,7 @@ __global__ void __launch_bounds__(kThreads, 1) td_sc_kernel(const SolveParams P)
     const int team = blockIdx.x / P.G;
     T.cta = blockIdx.x % P.G;
     T.epoch = 0; T.qepoch = 0;
+    T.sbase = smem_u32(smem_raw);
     T.xbase = P.xbuf + (size_t)team * P.xstride;
     T.qbase = P.qbox + (size_t)team * 64;
     T.oF1 = P.so.F1;

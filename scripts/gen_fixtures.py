@@ -75,7 +75,7 @@ def gen_c3():
     print(f"c3 collective: {res['kernel_evals']} evals, status {res['status']}, {time.time() - t0:.0f} s", flush=True)
     nt = len(res["t"])
     tau = O.relaxation_time(res["t"], res["F"][:, kpeak])
-    np.savez(os.path.join(GOLD, "c3_nk1000_eta0.5155.npz"),
+    np.savez_compressed(os.path.join(GOLD, "c3_nk1000_eta0.5155.npz"),
              **digest(res, cols, pick_rows(nt), dict(Nk=1000, eta=0.5155, kpeak=kpeak, tau_alpha=tau)))
     # tagged particle: F0 = 1, gamma = k^2 kBT/m, overdamped like the collective solve (test/test_tagged.jl:49-53 set-up)
     t0 = time.time()
@@ -84,7 +84,7 @@ def gen_c3():
                     kernel_tmap=np.arange(nt, dtype=np.int64))
     print(f"c3 tagged: {rs['kernel_evals']} evals, status {rs['status']}, {time.time() - t0:.0f} s", flush=True)
     taus = O.relaxation_time(rs["t"], rs["F"][:, kpeak])
-    np.savez(os.path.join(GOLD, "c3_tagged_nk1000_eta0.5155.npz"),
+    np.savez_compressed(os.path.join(GOLD, "c3_tagged_nk1000_eta0.5155.npz"),
              **digest(rs, cols, pick_rows(nt), dict(Nk=1000, eta=0.5155, kpeak=kpeak, tau_alpha=taus)))
 
 
@@ -97,7 +97,7 @@ def gen_c5(etas=(0.50, 0.5155, 0.52)):
         print(f"c5 eta={eta}: {res['kernel_evals']} evals, status {res['status']}, {time.time() - t0:.0f} s", flush=True)
         tau = O.relaxation_time(res["t"], res["F"][:, kpeak])
         ss = O.steady_state(O.sc3d(p["rho"], 1.0, 1.0, p["k"], p["Sk"]), p["gamma"], p["Sk"], tolerance=1e-12, max_iterations=10 ** 6)
-        np.savez(os.path.join(GOLD, f"c5_nk500_eta{eta}.npz"),
+        np.savez_compressed(os.path.join(GOLD, f"c5_nk500_eta{eta}.npz"),
                  **digest(res, cols, pick_rows(len(res["t"])), dict(Nk=500, eta=eta, kpeak=kpeak, tau_alpha=tau, f_steady=ss["F"],
                                                                    steady_iterations=np.int64(ss["iterations"]))))
 
@@ -127,7 +127,7 @@ def gen_c4(Nk=2000, N=4, dt=1e-4, t_max=1e-2):
     kk = [0, 1, Nk // 20, Nk // 6, Nk // 3, Nk // 2, Nk - 1]
     cols = sorted(set(int(i * ns * ns + e) for i in kk for e in (0, 1, 6, 15)))
     rows = sorted(set([0, 1, 2 * N, 2 * N + 1, nt // 2, nt - 2, nt - 1]))
-    np.savez(os.path.join(GOLD, f"c4_ns4_nk{Nk}_short.npz"),
+    np.savez_compressed(os.path.join(GOLD, f"c4_ns4_nk{Nk}_short.npz"),
              **digest(res, cols, rows, dict(Nk=Nk, ns=ns, N=N, dt=dt, t_max=t_max)))
 
 
