@@ -19,8 +19,19 @@ One "step" = one complete solve(equation, TimeDoublingSolver()) = one launch of 
              is single-threaded) on a bounded prefix of the same solve.  The reference itself is Julia and cannot
              run here.
 
-N > 1: the path shards over independent equations only -- every rank solves its own equation of the
-same configuration (weak scaling, no data-path collective); NCCL is used for the barrier and the max over ranks.
+N > 1: the contract line shards over independent equations only -- every rank solves its own equation of
+the same configuration (weak scaling, no data-path collective); NCCL is used for the barrier and the max over ranks.
+
+Besides the contract keys the line carries (all measured by this run, at every --gpus N):
+  parity_checked / parity   the timed host-buffer solve compared with the oracle's solution of the same equation
+             (tests/golden/c3_nk1000_eta0.5155.npz: F and K at 11 wavenumbers x all times and 12 times x all wavenumbers,
+             kernel_evals): max|dF| <= 1e-10 or the run fails.
+  sweep      BASELINE config 5 -- the 512-point packing-fraction sweep at Nk=500 sharded over the N ranks (strong scaling:
+             solves/s, wall, device ms per rank, kernel evaluations per rank, located eta_c).   --no-sweep skips it.
+  kshard     BASELINE config 4 -- the Ns=4, Nk=2000 mixture: evaluations/s of one equation k-sharded over the N ranks and,
+             for N >= 2, bitwise equality of the sharded solution with the single-GPU one.       --no-kshard skips it.
+  configs    config 1 (F2 schematic, scalar, CPU: reported only) and config 2 (Nk=100 on the device, microseconds/eval).
+  roofline_fp64, roofline.bound_actual   what the kernel is really bound by (it does not touch HBM during a solve).
 """
 import argparse
 import json
@@ -39,7 +50,8 @@ NK = 1000
 ETA = 0.5155
 WORKLOAD = ("config3: hard-sphere MCT, Percus-Yevick S(k), Nk=1000, eta=0.5155 (near eta_c), overdamped, "
             "TimeDoublingSolver(N=32, dt=1e-10, t_max=1e10, tol=1e-10)")
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 34611712 + 26191872      # profiles/ncu_full_r01_td_sc_kernel.csv
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 34611712 + 26191872      # dram__bytes_read.sum + dram__bytes_write.sum of one launch
+NCU_TRAFFIC_SOURCE = "profiles/ncu_full_r01_td_sc_kernel.csv"
 METRIC = "hs_mct_nk1000_kernel_evals_per_s"
 UNIT = "kernel evals/s"
 
@@ -104,33 +116,53 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_baseline_sample(seconds=15.0):
-    """The oracle on a bounded prefix of the SAME solve (first max_evals kernel evaluations of the Nk=1000 solve,
-    bootstrap included), 1 thread."""
+def _oracle_problem():
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle as O
     import importlib.util
     spec = importlib.util.spec_from_file_location("mct_sf", os.path.join(ROOT, "modecouplingtheory.jl_b200", "structure_factors.py"))
     sf = importlib.util.module_from_spec(spec); spec.loader.exec_module(sf)
     p = problem(sf)
-    kern = O.sc3d(p["rho"], 1.0, 1.0, p["k"], p["Sk"])
-    # calibrate with a few evaluations, then run the real solver for a bounded number of evaluations
-    t0 = time.perf_counter(); kern.eval_repeat(p["F0"], 3); per_eval = (time.perf_counter() - t0) / 3
-    n = max(8, int(seconds / per_eval) - (2 * 32 + 1))
+    return O, p, O.sc3d(p["rho"], 1.0, 1.0, p["k"], p["Sk"])
+
+
+_BOOT = {}
+
+
+def cpu_baseline_sample(n_evals=200):
+    """The oracle on a bounded prefix of the SAME solve, 1 thread: `n_evals` fixed-point kernel evaluations of the main loop
+    (what 53 197 of the solve's 53 262 evaluations are), timed as (prefix with n_evals) - (prefix with 1), i.e. without the
+    2N-step Euler bootstrap, whose O(step) convolution would dominate a short prefix; the bootstrap is reported beside it."""
+    O, p, kern = _oracle_problem()
+    solve = lambda n: O.td_solve(kern, 0.0, 1.0, p["gamma"], 0.0, p["F0"], p["dF0"], max_iterations=10 ** 6, max_evals=n)
+    if "s" not in _BOOT:                      # bootstrap (65 evaluations + Euler convolutions) + 1 evaluation: timed once
+        t0 = time.perf_counter(); solve(1); _BOOT["s"] = time.perf_counter() - t0
+    t0 = time.perf_counter(); res = solve(1 + n_evals); wall = time.perf_counter() - t0
+    done = res["kernel_evals"] - 1
+    rate = done / max(wall - _BOOT["s"], 1e-9)
+    return rate, (f"{done} fixed-point kernel evaluations of the same Nk=1000 solve in {wall - _BOOT['s']:.1f} s "
+                  f"(bootstrap of 65 evaluations timed separately: {_BOOT['s']:.1f} s; whole solve extrapolated: "
+                  f"{53197 / rate + _BOOT['s']:.0f} s)")
+
+
+def config1_f2_on_cpu():
+    """BASELINE config 1 (README.md:30-47): SchematicF2Kernel(3.999), scalar MemoryEquation, TimeDoublingSolver defaults --
+    stays on the CPU, reported for completeness: oracle wall time and evaluations."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as O
     t0 = time.perf_counter()
-    res = O.td_solve(kern, 0.0, 1.0, p["gamma"], 0.0, p["F0"], p["dF0"], max_iterations=10 ** 6, max_evals=n)
+    r = O.td_solve(O.f2(3.999), 1.0, 0.0, 1.0, 0.0, np.array([1.0]), np.array([0.0]), t_max=1e10, scalar_mode=True)
     wall = time.perf_counter() - t0
-    evals = res["kernel_evals"] + 2 * 32 + 1          # + bootstrap (2N) and K0 evaluations, not counted by solver.kernel_evals
-    return evals / wall, f"first {res['kernel_evals']} fixed-point kernel evaluations (+{2 * 32 + 1} bootstrap) of the same Nk=1000 solve, {wall:.1f} s"
+    return {"workload": "config1: SchematicF2Kernel(nu=3.999) scalar, TimeDoublingSolver defaults, CPU oracle (reported, not accelerated)",
+            "wall_ms": 1e3 * wall, "kernel_evals": int(r["kernel_evals"]), "F_end": float(r["F"][-1, 0])}
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
-    vals = []
-    sample = ""
-    for i in range(args.warmup + args.steps):
-        v, sample = cpu_baseline_sample(seconds=max(3.0, min(20.0, 60.0 / max(1, args.warmup + args.steps))))
+    vals, sample = [], ""
+    for i in range(args.warmup + args.steps):       # every step: one bounded sample (200 fixed-point evaluations, ~13 s)
+        v, sample = cpu_baseline_sample(200)
         if i >= args.warmup:
             vals.append(v)
     value = float(np.mean(vals))
@@ -140,15 +172,67 @@ def run_reference(args, rank):
             "config": {"workload": WORKLOAD, "note": "reference = ModeCouplingTheory.jl (Julia, not installable here: no julia binary, "
                        "no network); timed instead: oracle/mct_oracle.c, the C restatement in the reference's operation order"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample +
-                             "; 1 thread because the reference hot path is single-threaded (@turbo, no @threads)"},
+                             "; 1 thread because the reference hot path is single-threaded (@turbo, no @threads)",
+                             "spread": {"min": float(np.min(vals)), "max": float(np.max(vals)), "samples": len(vals)}},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
-def run_mc_workload(args, pkg, torch, dist, rank, world, dev):
-    """Config 4: ONE multi-component equation (Ns=4 hard-sphere mixture, Nk=2000), k-sharded over the ranks: rank r
-    evaluates the lines L = r (mod world) of the vertex sum and stores their sums into every rank's buffer over NVLink
-    from inside its persistent kernel.  Strong scaling; the time axis is shortened (t_max) so that a step stays bounded."""
+def sweep_record(args, pkg, torch, dist, rank, world, dev):
+    """Config 5: `points` packing fractions in [0.50, 0.53] at Nk = sweep_nk, sharded over the ranks (strong scaling).
+    eta_c is located on the grid (steady-state bisection on the device), the measured cost model deals the points to ranks
+    longest-first and sorts every rank's queue, outliers get a whole-GPU team (sweep.py); no data-path collective, one final
+    gather of the observable.  The wall clock includes everything: eta_c location, table construction, uploads, solves,
+    downloads of the observable, the gather."""
+    sw = pkg.sweep
+    etas = np.linspace(0.50, 0.53, args.points)
+    kpeak = int(np.argmin(np.abs(pkg.structure_factors.wavenumber_grid(args.sweep_nk) - 7.0)))
+    nt = pkg.TimeDoublingSolver().output_len()
+    obs = lambda sol: np.array([sol.F[-1, 0] / sol.F[0, 0]])
+    slice_ = dict(times=[0, nt - 1], dofs=[kpeak], K=False)        # two numbers per solution cross PCIe
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    eta_c = sw.locate_eta_c(pkg, args.sweep_nk, dev)
+    t_loc = time.perf_counter() - t0
+    cost = sw.expected_cost(etas, eta_c)
+    big = sw.outliers(cost, world)
+    mine = sw.partition(cost, world, rank)
+    pos_big = [mine.index(i) for i in big if i in mine]
+    vals, evals_pt, ms = sw.run_sweep(pkg, etas[mine], args.sweep_nk, dev, observable=obs, download=slice_, costs=cost[mine], big_team=pos_big)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    per_rank = torch.zeros(world, 3, dtype=torch.float64, device=f"cuda:{dev}")
+    per_rank[rank, 0], per_rank[rank, 1], per_rank[rank, 2] = wall, ms, float(evals_pt.sum())
+    if world > 1:
+        dist.all_reduce(per_rank, op=dist.ReduceOp.SUM)
+    allv = sw.gather(mine, vals, len(etas), world, dist if world > 1 else None)
+    wall_all = time.perf_counter() - t0
+    w = torch.tensor([wall_all], dtype=torch.float64, device=f"cuda:{dev}")
+    if world > 1:
+        dist.all_reduce(w, op=dist.ReduceOp.MAX)
+    pr = per_rank.cpu().numpy()
+    nonerg = allv[:, 0] > 0.1
+    return {"workload": f"config5: {args.points}-point packing-fraction sweep eta in [0.50, 0.53], Nk={args.sweep_nk}, overdamped, "
+                        "TimeDoublingSolver defaults (max_iterations 1e6)",
+            "solves_per_s": args.points / w.item(), "wall_s": w.item(), "n_gpus": world, "scaling": "strong",
+            "device_ms_per_rank": [round(x, 1) for x in pr[:, 1].tolist()], "wall_s_per_rank": [round(x, 3) for x in pr[:, 0].tolist()],
+            "kernel_evals_per_rank": [int(x) for x in pr[:, 2].tolist()], "kernel_evals_total": int(pr[:, 2].sum()),
+            "device_ms_max_over_min": float(pr[:, 1].max() / max(pr[:, 1].min(), 1e-9)),
+            "eta_c_located_by_steady_state": eta_c, "eta_c_location_s": t_loc,
+            "first_nonergodic_point": float(etas[np.argmax(nonerg)]) if nonerg.any() else None,
+            "whole_gpu_team_points": [float(etas[i]) for i in big],
+            "sharding": "longest-first onto the least loaded rank by the measured cost model, sorted queue per rank, no data-path "
+                        "collective, final gather of one observable"}
+
+
+def kshard_record(args, pkg, torch, dist, rank, world, dev):
+    """Config 4: ONE multi-component equation (Ns=4 hard-sphere mixture, Nk=2000) on a shortened time axis.  N = 1: evaluations/s
+    of the single-GPU solve.  N >= 2: the same equation k-sharded over the ranks (rank r evaluates its share of the lines of
+    the vertex sum, the sums travel by device-initiated NVLink loads from CUDA-IPC-mapped peer buffers, everything else is
+    replicated) -- evaluations/s, and the sharded trajectory compared BITWISE with the single-GPU trajectory of the same
+    library on every rank."""
     sf = pkg.structure_factors
     ns, Nk = 4, args.mc_nk
     diam = np.array([0.7, 0.8, 0.9, 1.0]); x = np.full(ns, 0.25)
@@ -161,79 +245,83 @@ def run_mc_workload(args, pkg, torch, dist, rank, world, dev):
     kern = pkg.MultiComponentModeCouplingKernel(rho, 1.0, m, k, Sk, device=dev)
     eq = pkg.MemoryEquation(1.0, 0.0, gamma, np.zeros((Nk, ns, ns)), Sk, np.zeros((Nk, ns, ns)), kern)
     solver = pkg.TimeDoublingSolver(N=4, dt=1e-4, t_max=args.mc_tmax, tolerance=1e-10, max_iterations=10 ** 6)
-    dev_eq = pkg.api.create_equation(eq, solver)
+
+    def timed(dev_eq):
+        ms_all = []
+        for _ in range(args.mc_warmup + args.mc_steps):      # every pass is the whole solve again from F0
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            evals, ms = pkg.api.solve_resident(dev_eq)
+            ms_all.append(ms)
+        t = torch.tensor([float(np.mean(ms_all[args.mc_warmup:]))], dtype=torch.float64, device=f"cuda:{dev}")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return evals + 2 * solver.N + 1, t.item()
+
+    single = pkg.api.create_equation(eq, solver)
+    evals1, ms1 = timed(single)
+    F1 = pkg.api.download_solution(single, solver, kern.dof).F
+    single.close()
+    rec = {"workload": f"config4: MultiComponentModeCouplingKernel Ns=4 (diameters 0.7/0.8/0.9/1.0, equal fractions, phi=0.50), Nk={Nk}, "
+                       f"Newtonian, TimeDoublingSolver(N=4, dt=1e-4, t_max={args.mc_tmax}, tol=1e-10)",
+           "n_gpus": world, "scaling": "strong", "kernel_evals": int(evals1),
+           "single_gpu_evals_per_s": evals1 / (ms1 * 1e-3), "single_gpu_ms": ms1,
+           "fp64_ginstr_per_s_single_gpu": 14.0 * ns * ns * Nk * Nk * 0.75 * evals1 / (ms1 * 1e-3) / 1e9, "fp64_peak_ginstr_per_s": 17700.0}
     if world > 1:
         def all_gather(b):
             out = [None] * world
             dist.all_gather_object(out, b)
             return out
-        pkg.api.shard_equation(dev_eq, rank, world, all_gather)
-    ms_all = []
-    for _ in range(args.mc_warmup + args.mc_steps):      # every pass is the whole solve again from F0
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        evals, ms = pkg.api.solve_resident(dev_eq)
-        ms_all.append(ms)
-    ms = float(np.mean(ms_all[args.mc_warmup:]))
-    stats = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{dev}")
-    if world > 1:
-        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
-    if rank == 0:
-        ms_max = stats.item()
-        n_out = solver.output_len()
-        total_evals = evals + 2 * solver.N + 1
-        print(json.dumps({
-            "metric": "mc_ns4_kernel_evals_per_s", "value": total_evals / (ms_max * 1e-3), "unit": "kernel evals/s", "n_gpus": world,
-            "steps": args.mc_steps, "warmup": args.mc_warmup, "ms_per_step": ms_max, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic (Percus-Yevick hard-sphere mixture, Baxter factorisation)",
-            "config": {"workload": f"config4: MultiComponentModeCouplingKernel Ns=4 (diameters 0.7/0.8/0.9/1.0, equal fractions, phi=0.50), "
-                       f"Nk={Nk}, Newtonian, TimeDoublingSolver(N=4, dt=1e-4, t_max={args.mc_tmax}, tol=1e-10); k-sharded over {world} GPU(s)",
-                       "kernel_evals": total_evals, "output_times": n_out,
-                       "fp64_instr_per_eval": 14.0 * ns * ns * Nk * Nk * 0.75,      # 14 per (iq,ip,a,b) entry, 3/4 Nk^2 entries walked
-                       "achieved_fp64_ginstr_per_s": 14.0 * ns * ns * Nk * Nk * 0.75 * total_evals / (ms_max * 1e-3) / 1e9,
-                       "fp64_peak_ginstr_per_s": 17700.0,                   # profiles/fp64_bench.txt (an FMA counts once)
-                       "exchange": "device-initiated stores of the line sums into CUDA-IPC-mapped peer buffers (no collective call)" if world > 1 else "none"}}),
-            flush=True)
+        sharded = pkg.api.create_equation(eq, solver)
+        pkg.api.shard_equation(sharded, rank, world, all_gather)
+        evalsN, msN = timed(sharded)
+        FN = pkg.api.download_solution(sharded, solver, kern.dof).F
+        same = torch.tensor([1.0 if (evalsN == evals1 and np.array_equal(FN, F1)) else 0.0], dtype=torch.float64, device=f"cuda:{dev}")
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        sharded.close()
+        rec.update({"evals_per_s": evalsN / (msN * 1e-3), "ms": msN, "speedup_over_single_gpu": ms1 / msN,
+                    "bitwise_equal_to_single_gpu": bool(same.item() == 1.0),
+                    "exchange": "device-initiated pull of the line sums from CUDA-IPC-mapped peer buffers over NVLink (no collective call)"})
+    else:
+        rec.update({"evals_per_s": evals1 / (ms1 * 1e-3), "ms": ms1, "bitwise_equal_to_single_gpu": None})
+    kern.close()
+    return rec
 
 
-def run_sweep_workload(args, pkg, torch, dist, rank, world, dev):
-    """Config 5: `points` packing fractions in [0.50, 0.53] at Nk = sweep_nk, sharded over the ranks (cost-aware snake
-    partition), `solve_batch` per GPU (one persistent launch, teams pull equations from a queue), final gather of
-    F(k_peak, t_end) to locate eta_c.  One step = the whole sweep."""
-    sw = pkg.sweep
-    etas = np.linspace(0.50, 0.53, args.points)
-    mine = sw.partition(sw.expected_cost(etas), world, rank)
-    kpeak = int(np.argmin(np.abs(pkg.structure_factors.wavenumber_grid(args.sweep_nk) - 7.0)))
-    nt = pkg.TimeDoublingSolver().output_len()
-    # only F(k_peak, t=0) and F(k_peak, t_end) of every solution cross PCIe (mct_equation_download_slice)
-    obs = lambda sol: np.array([sol.F[-1, 0] / sol.F[0, 0]])
-    slice_ = dict(times=[0, nt - 1], dofs=[kpeak], K=False)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    vals, evals, ms = sw.run_sweep(pkg, etas[mine], args.sweep_nk, dev, batch=64, observable=obs, download=slice_)
-    torch.cuda.synchronize()
-    wall = time.perf_counter() - t0
-    stats = torch.tensor([wall, ms], dtype=torch.float64, device=f"cuda:{dev}")
-    tot = torch.tensor([float(evals)], dtype=torch.float64, device=f"cuda:{dev}")
-    if world > 1:
-        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    allv = sw.gather(mine, vals, len(etas), world, dist if world > 1 else None)
-    if rank == 0:
-        wall_max, ms_max = stats.tolist()
-        nonerg = allv[:, 0] > 0.1
-        eta_c = float(etas[np.argmax(nonerg)]) if nonerg.any() else None
-        print(json.dumps({
-            "metric": "eta_sweep_solves_per_s", "value": args.points / wall_max, "unit": "solves/s", "n_gpus": world, "steps": 1,
-            "warmup": 0, "ms_per_step": 1e3 * wall_max, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic (analytic Percus-Yevick hard-sphere S(k))",
-            "config": {"workload": f"config5: {args.points}-point packing-fraction sweep eta in [0.50, 0.53], Nk={args.sweep_nk}, "
-                       "overdamped, TimeDoublingSolver defaults; wall clock incl. table construction, uploads and trajectory downloads",
-                       "device_ms_max_over_ranks": ms_max, "kernel_evals_total": tot.item(), "eta_c_located": eta_c,
-                       "sharding": "cost-aware snake partition over ranks, no data-path collective, final gather of one observable"}}), flush=True)
+def config2_record(pkg, dev):
+    """BASELINE config 2: Nk=100, eta=0.51, defaults -- the launch-bound regime: one persistent launch, microseconds per evaluation."""
+    sf = pkg.structure_factors
+    p = problem(sf, eta=0.51, Nk=100)
+    kern = pkg.ModeCouplingKernel(p["rho"], 1.0, 1.0, p["k"], p["Sk"], device=dev)
+    eq = pkg.MemoryEquation(0.0, 1.0, p["gamma"], 0.0, p["F0"], p["dF0"], kern)
+    solver = pkg.TimeDoublingSolver(max_iterations=10 ** 6)
+    d = pkg.api.create_equation(eq, solver)
+    ms = []
+    for _ in range(4):
+        ev, t = pkg.api.solve_resident(d)
+        ms.append(t)
+    d.close(); kern.close()
+    return {"workload": "config2: hard-sphere MCT, Nk=100, eta=0.51, TimeDoublingSolver defaults, one persistent launch (thread-block cluster team)",
+            "kernel_evals": int(ev), "solve_ms": float(np.mean(ms[1:])), "us_per_eval": 1e3 * float(np.mean(ms[1:])) / ev,
+            "evals_per_s": ev / (float(np.mean(ms[1:])) * 1e-3)}
+
+
+def parity_against_fixture(t, F, K, evals):
+    """The host buffers of the timed end-to-end solve against the oracle's solution of the same equation (scripts/gen_fixtures.py)."""
+    path = os.path.join(ROOT, "tests", "golden", "c3_nk1000_eta0.5155.npz")
+    if not os.path.exists(path):
+        return False, {"error": "tests/golden/c3_nk1000_eta0.5155.npz missing"}
+    fx = np.load(path)
+    cols, rows = fx["cols"], fx["rows"]
+    dF = max(np.max(np.abs(F[:, cols] - fx["F_cols"])), np.max(np.abs(F[rows, :] - fx["F_rows"])))
+    scaleK = np.max(np.abs(fx["K_rows"]))
+    dK = max(np.max(np.abs(K[:, cols] - fx["K_cols"])), np.max(np.abs(K[rows, :] - fx["K_rows"]))) / scaleK
+    ds = float(np.max(np.abs(F.sum(axis=1) - fx["F_sum_t"])) / F.shape[1])
+    ok = bool(np.array_equal(t, fx["t"]) and dF <= 1e-10 and int(evals) == int(fx["kernel_evals"]))
+    return ok, {"against": "tests/golden/c3_nk1000_eta0.5155.npz (CPU oracle, full solve)", "max_abs_dF": float(dF), "tolerance": 1e-10,
+                "max_abs_dK_over_maxK": float(dK), "checksum_dev_per_entry": ds, "kernel_evals": int(evals),
+                "kernel_evals_oracle": int(fx["kernel_evals"]), "time_grid_identical": bool(np.array_equal(t, fx["t"]))}
 
 
 def main():
@@ -243,8 +331,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="solve", choices=["solve", "sweep", "mc"],
-                    help="solve: config 3 (the contract line).  sweep: config 5, the packing-fraction sweep sharded over the ranks")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the config-5 sub-record")
+    ap.add_argument("--no-kshard", action="store_true", help="skip the config-4 sub-record")
     ap.add_argument("--points", type=int, default=512)
     ap.add_argument("--sweep-nk", type=int, default=500)
     ap.add_argument("--mc-nk", type=int, default=2000)
@@ -269,17 +357,6 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = local_rank
-
-    if args.workload == "mc":
-        run_mc_workload(args, pkg, torch, dist, rank, world, dev)
-        if world > 1:
-            dist.destroy_process_group()
-        return
-    if args.workload == "sweep":
-        run_sweep_workload(args, pkg, torch, dist, rank, world, dev)
-        if world > 1:
-            dist.destroy_process_group()
-        return
 
     p = problem(pkg.structure_factors)
     kern = pkg.ModeCouplingKernel(p["rho"], 1.0, 1.0, p["k"], p["Sk"], device=dev)
@@ -337,6 +414,12 @@ def main():
         ev, s = e2e_step()
         e2e_evals += ev; e2e_s += s
     barrier()
+    parity_ok, parity = parity_against_fixture(host_out[0], host_out[1], host_out[2], ev)      # the LAST timed solve's host buffers
+    kern.close()
+
+    # ---- the other BASELINE configurations, measured by every run (all ranks take part in the sharded ones)
+    sweep_rec = None if args.no_sweep else sweep_record(args, pkg, torch, dist, rank, world, dev)
+    kshard_rec = None if args.no_kshard else kshard_record(args, pkg, torch, dist, rank, world, dev)
 
     # ---- max over ranks, whole-job aggregate
     stats = torch.tensor([ms_tot, e2e_s], dtype=torch.float64, device=f"cuda:{dev}")
@@ -351,32 +434,52 @@ def main():
         peak, peak_src = measured_peak()
         bytes_per_eval = 24.0 * NK * NK + 16.0 * NK
         launch_ms = ms_tot / args.steps
-        achieved = (evals_tot / args.steps) * bytes_per_eval / (launch_ms * 1e-3) / 1e9
+        evals_per_solve = evals_tot / args.steps
+        achieved = evals_per_solve * bytes_per_eval / (launch_ms * 1e-3) / 1e9
+        # FP64 instructions the kernel really issues per evaluation: every warp walks U units of 32 positions x 4 rows,
+        # 4 DMUL + 12 DFMA per lane and unit (padding units included) -- G*8*U*32*16 lane-instructions
+        geo = pkg.api.last_geometry() if hasattr(pkg.api, "last_geometry") else None
+        fp64_lane_instr = (148 * 8 * 8 * 32 * 16) if not geo else geo["G"] * 8 * geo["U"] * 32 * 16
+        fp64_rate = fp64_lane_instr * evals_per_solve / (launch_ms * 1e-3)
         h2d = 6 * NK * 8
         d2h = (2 * nt * NK + nt) * 8
         line = {
             "metric": METRIC, "value": evals_all / (ms_max * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic (analytic Percus-Yevick hard-sphere S(k))",
-            "config": {"workload": WORKLOAD, "kernel_evals_per_solve": evals_tot / args.steps, "output_times": nt,
+            "config": {"workload": WORKLOAD, "kernel_evals_per_solve": evals_per_solve, "output_times": nt,
                        "solve_wall_ms_device": launch_ms, "l2": "256 MiB buffer written between timed iterations (L2 flush)",
                        "sharding": "one independent equation per GPU, no data-path collective" if world > 1 else "single GPU"},
             "e2e": {"value": e2e_evals_all / e2e_max, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "solve_wall_ms": 1e3 * e2e_max / args.steps},
             "gpu_launches": int(launches_all),
+            "parity_checked": parity_ok, "parity": parity,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH,
                          "kernel": "td_sc_kernel (one persistent cooperative launch per solve)",
                          "algorithmic_bytes_per_eval": bytes_per_eval, "peak_source": peak_src,
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one td_sc_kernel launch, ncu --set full capture of "
-                                           "the Nk=1000 solve (profiles/ncu_full_r01_td_sc_kernel.csv); not re-measured by this run",
-                         "note": "vertex tables stay in registers + shared memory for the whole solve; DRAM traffic per launch is "
-                                 "one table load + the trajectory store, ~6000x less than the algorithmic bytes"},
+                                           "the Nk=1000 solve (" + NCU_TRAFFIC_SOURCE + "); not re-measured by this run",
+                         "bound_actual": "latency: one inter-SM all-gather through L2 per evaluation (arrival counter + one load round trip, "
+                                         "~1.1 us) and per-warp instruction issue at 8 warps/SM; neither HBM nor FP64 nor shared memory binds",
+                         "note": "the vertex tables stay in tensor memory (TMEM) for the whole solve, so 'achieved' is an HBM-equivalent "
+                                 "figure of the algorithmic bytes (SURVEY 8d); DRAM traffic per launch is one table load + the trajectory "
+                                 "store, ~10^4 x less than the algorithmic bytes"},
+            "roofline_fp64": {"achieved": fp64_rate / 1e12, "peak": 17.7, "unit": "T FP64 instr/s (an FMA counts once)", "frac": fp64_rate / 17.7e12,
+                              "peak_source": "measured (profiles/fp64_bench.txt: 60.9 DFMA lanes/clk/SM)",
+                              "fp64_lane_instructions_per_eval": fp64_lane_instr},
             "clocks": clocks,
         }
+        if sweep_rec is not None:
+            line["sweep"] = sweep_rec
+        if kshard_rec is not None:
+            line["kshard"] = kshard_rec
+        line["configs"] = {"config1": config1_f2_on_cpu(), "config2": config2_record(pkg, dev)}
         if not args.no_cpu_baseline:
             v, sample = cpu_baseline_sample()
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample}
         print(json.dumps(line), flush=True)
+        if not parity_ok:
+            raise SystemExit("bench.py: the timed solve does not match the oracle fixture: " + json.dumps(parity))
     if world > 1:
         dist.destroy_process_group()
 

@@ -246,8 +246,9 @@ static int choose_geometry(mct_kernel_t h, int n_eq, TeamLayout **out, int *ntea
     const long long units = layout_total_units(Nk, sym);
     const int g_cap = std::max(1, std::min(n_sm, Nk / 2));               // at least two rows per CTA
     const int g_min = (Nk + kThreads - 1) / kThreads;                    // one owner thread per row
-    // on-chip capacity of one CTA in units per warp: registers + what shared memory can hold
-    const int u_chip = td_sc_max_reg_units(Nk) + (int)((h->smem_optin - 56 * 1024 - (size_t)48 * Nk) / ((size_t)kWarps * kUV * 32 * 8));
+    // on-chip capacity of one CTA in units per warp: tensor memory (10) + registers + what shared memory can hold
+    const int u_tmem = env_int("MCT_TMEM", 1) ? std::min(10, env_int("MCT_MAX_TMEM_UNITS", 10)) : 0;
+    const int u_chip = u_tmem + td_sc_max_reg_units(Nk) + (int)((h->smem_optin - 72 * 1024 - (size_t)48 * Nk) / ((size_t)kWarps * kUV * 32 * 8));
     int G_fit = (int)std::min<long long>(g_cap, std::max<long long>(g_min, (units + (long long)kWarps * u_chip - 1) / ((long long)kWarps * u_chip)));
     int G;
     if (n_eq == 1) {
