@@ -198,7 +198,7 @@ def sweep_record(args, pkg, torch, dist, rank, world, dev):
     t_loc = time.perf_counter() - t0
     cost = sw.expected_cost(etas, eta_c)
     big = sw.outliers(cost, world)
-    mine = sw.partition(cost, world, rank)
+    mine = sw.partition(sw.weighted_costs(cost, world), world, rank)
     pos_big = [mine.index(i) for i in big if i in mine]
     vals, evals_pt, ms = sw.run_sweep(pkg, etas[mine], args.sweep_nk, dev, observable=obs, download=slice_, costs=cost[mine], big_team=pos_big)
     torch.cuda.synchronize()
@@ -220,7 +220,7 @@ def sweep_record(args, pkg, torch, dist, rank, world, dev):
             "device_ms_per_rank": [round(x, 1) for x in pr[:, 1].tolist()], "wall_s_per_rank": [round(x, 3) for x in pr[:, 0].tolist()],
             "kernel_evals_per_rank": [int(x) for x in pr[:, 2].tolist()], "kernel_evals_total": int(pr[:, 2].sum()),
             "device_ms_max_over_min": float(pr[:, 1].max() / max(pr[:, 1].min(), 1e-9)),
-            "eta_c_located_by_steady_state": eta_c, "eta_c_location_s": t_loc,
+            "eta_c_located_by_steady_state": eta_c, "eta_c_location_s": t_loc, "host_timing_rank0": {k: round(v, 3) for k, v in sw.run_sweep.last_timing.items()},
             "first_nonergodic_point": float(etas[np.argmax(nonerg)]) if nonerg.any() else None,
             "whole_gpu_team_points": [float(etas[i]) for i in big],
             "sharding": "longest-first onto the least loaded rank by the measured cost model, sorted queue per rank, no data-path "

@@ -37,6 +37,62 @@ enum KernelType { K_SC3D = 1, K_TAGGED3D = 2, K_MC3D = 3, K_DDIM = 5 };
 using GeomKey = std::tuple<int, int, int, int>;
 static std::mutex g_geom_mutex;
 static std::map<GeomKey, TeamLayout *> g_geoms;
+static std::mutex g_stream_mutex;
+static std::vector<cudaStream_t> g_stream_pool[64];
+static unsigned g_stream_next[64];
+constexpr int kStreamsPerDevice = 8;
+
+
+// ---- device memory arena -----------------------------------------------------------------------------------------------
+// cudaMalloc / cudaFree synchronise with the driver and cost milliseconds each on these boxes (measured: 12 ms per kernel
+// handle created, 14 ms per handle destroyed -- 10 s of a 512-point sweep).  Every buffer of this file therefore comes from
+// large chunks that are obtained once and never returned: blocks are carved off a chunk and, when released, kept in
+// exact-size bins (a sweep asks for the same few sizes again and again).  Buffers exported through CUDA IPC (the k-shard
+// exchange) bypass the arena: an IPC handle names a whole allocation.
+namespace {
+struct Arena {
+    struct Chunk { char *base; size_t size, used; };
+    std::mutex mu;
+    std::vector<Chunk> chunks[64];
+    std::map<size_t, std::vector<void *>> bins[64];
+    std::map<void *, std::pair<int, size_t>> live;          // block -> (device, rounded size)
+    static size_t round_up(size_t b) { return (std::max<size_t>(b, 1) + 511) & ~(size_t)511; }
+    cudaError_t alloc(void **p, size_t bytes) {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        dev &= 63;
+        const size_t n = round_up(bytes);
+        std::lock_guard<std::mutex> lock(mu);
+        auto it = bins[dev].find(n);
+        if (it != bins[dev].end() && !it->second.empty()) { *p = it->second.back(); it->second.pop_back(); live[*p] = {dev, n}; return cudaSuccess; }
+        for (Chunk &c : chunks[dev])
+            if (c.size - c.used >= n) { *p = c.base + c.used; c.used += n; live[*p] = {dev, n}; return cudaSuccess; }
+        const size_t csize = std::max<size_t>(n, (size_t)512 << 20);
+        void *base = nullptr;
+        e = (cudaMalloc)(&base, csize);
+        if (e != cudaSuccess) { cudaGetLastError(); if (csize > n) e = (cudaMalloc)(&base, n); if (e != cudaSuccess) return e; chunks[dev].push_back({(char *)base, n, n}); }
+        else chunks[dev].push_back({(char *)base, csize, n});
+        *p = base; live[*p] = {dev, n};
+        return cudaSuccess;
+    }
+    cudaError_t release(void *p) {
+        if (!p) return cudaSuccess;
+        std::lock_guard<std::mutex> lock(mu);
+        auto it = live.find(p);
+        if (it == live.end()) return (cudaFree)(p);         // not ours (IPC buffers)
+        bins[it->second.first][it->second.second].push_back(p);
+        live.erase(it);
+        return cudaSuccess;
+    }
+};
+Arena g_arena;
+inline cudaError_t raw_cuda_malloc(void **p, size_t bytes) { return cudaMalloc(p, bytes); }      // a real allocation (CUDA IPC)
+template <class T> cudaError_t arena_malloc(T **p, size_t bytes) { return g_arena.alloc((void **)p, bytes); }
+inline cudaError_t arena_free(void *p) { return g_arena.release(p); }
+}  // namespace
+#define cudaMalloc arena_malloc
+#define cudaFree arena_free
 
 }  // namespace mct
 
@@ -145,13 +201,34 @@ static int new_handle(mct_kernel_t *out, int type, int device, int Nk, const dou
     MCT_CUDA(cudaGetDeviceCount(&ndev));
     MCT_REQUIRE(device >= 0 && device < ndev, MCT_BAD_ARGUMENT, "no such CUDA device");
     MCT_CUDA(cudaSetDevice(device));
-    cudaDeviceProp prop;
-    MCT_CUDA(cudaGetDeviceProperties(&prop, device));
-    MCT_REQUIRE(prop.major == 10, MCT_CUDA_ERROR, "libmct_sm100a needs an sm_100 (B200) device; there is no CPU or other-GPU fallback");
+    // device attributes, queried once per device (cudaGetDeviceProperties costs ~20 ms per call: 10 s for a 512-point sweep)
+    struct DevInfo { int major = -1, n_sm = 0, smem_optin = 0; };
+    static DevInfo g_dev[64];
+    DevInfo &di = g_dev[device & 63];
+    if (di.major < 0) {
+        int major = 0;
+        MCT_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+        MCT_CUDA(cudaDeviceGetAttribute(&di.n_sm, cudaDevAttrMultiProcessorCount, device));
+        MCT_CUDA(cudaDeviceGetAttribute(&di.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+        di.major = major;
+    }
+    MCT_REQUIRE(di.major == 10, MCT_CUDA_ERROR, "libmct_sm100a needs an sm_100 (B200) device; there is no CPU or other-GPU fallback");
     mct_kernel_t h = new mct_kernel_s();
     h->type = type; h->device = device; h->Nk = Nk;
-    h->n_sm = prop.multiProcessorCount; h->smem_optin = prop.sharedMemPerBlockOptin;
-    cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    h->n_sm = di.n_sm; h->smem_optin = (size_t)di.smem_optin;
+    // Kernel handles share a small set of streams per device (round robin): creating a stream costs ~9 ms on these boxes
+    // (4.6 s for the 512 handles of a sweep).  Work of handles that share a stream is merely serialised.
+    cudaError_t e = cudaSuccess;
+    {
+        std::lock_guard<std::mutex> lock(g_stream_mutex);
+        auto &pool = g_stream_pool[device & 63];
+        if ((int)pool.size() < kStreamsPerDevice) {
+            cudaStream_t st = nullptr;
+            e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+            if (e == cudaSuccess) pool.push_back(st);
+        }
+        if (e == cudaSuccess) h->stream = pool[g_stream_next[device & 63]++ % pool.size()];
+    }
     if (e == cudaSuccess) e = cudaMalloc(&h->d_k, Nk * sizeof(double));
     if (e == cudaSuccess) e = cudaMemcpyAsync(h->d_k, k, Nk * sizeof(double), cudaMemcpyHostToDevice, h->stream);
     if (e != cudaSuccess) { delete h; return cuda_fail(e, "new_handle", __FILE__, __LINE__); }
@@ -381,24 +458,29 @@ static int run_batch(int n, mct_equation_t *eqs, int mode, double tol, long long
         e.status = q->d_status; e.kernel_evals = q->d_evals;
     }
     SolveParams P{};
-    const int fabric = (L->G > 1 && L->G <= 16 && env_int("MCT_CLUSTER", 1)) ? 1 : 0;
-    const Residency res = choose_residency(*L, h0->smem_optin, fabric);
-    P.Nk = h0->Nk; P.G = L->G; P.N = eqs[0]->opts.N; P.nblocks = eqs[0]->nblocks; P.n_eq = n; P.nteams = nteams;
-    P.second_order = eqs[0]->second_order;
-    P.dt0 = eqs[0]->opts.dt; P.tol = tol; P.max_iter = max_iter;
-    P.U = L->U; P.UR = res.UR; P.UT = res.UT; P.US = res.US; P.lane_cap = res.lane_cap;
-    P.rows_max = L->rows_max; P.rb_max = L->rb_max; P.ent_max = L->ent_max;
-    P.udesc = L->d_udesc; P.cta_meta = L->d_cta_meta; P.ent_begin = L->d_ent_begin; P.warp_ent = L->d_warp_ent; P.row_owner = L->d_row_owner;
-    P.xbuf_words = L->xbuf_words; P.xrows = L->xrows; P.fabric = fabric;
-    P.xstride = 4LL * L->xbuf_words + 16;      // four rotating buffers + the arrival counter (own line)
-    P.dbg = env_int("MCT_DBG", 0);
-    P.snap_epoch = env_int("MCT_SNAP_EPOCH", 1000);
-    P.spin_limit_cycles = (long long)env_int("MCT_SPIN_LIMIT_MS", 2000) * 2000000LL;
-    if (fabric == 1) {
+    int fabric = (L->G > 1 && L->G <= 16 && env_int("MCT_CLUSTER", 1)) ? 1 : 0;
+    const int nteams_wanted = nteams;
+    for (;;) {
+        const Residency res = choose_residency(*L, h0->smem_optin, fabric);
+        P = SolveParams{};
+        P.Nk = h0->Nk; P.G = L->G; P.N = eqs[0]->opts.N; P.nblocks = eqs[0]->nblocks; P.n_eq = n; P.nteams = nteams;
+        P.second_order = eqs[0]->second_order;
+        P.dt0 = eqs[0]->opts.dt; P.tol = tol; P.max_iter = max_iter;
+        P.U = L->U; P.UR = res.UR; P.UT = res.UT; P.US = res.US; P.lane_cap = res.lane_cap;
+        P.rows_max = L->rows_max; P.rb_max = L->rb_max; P.ent_max = L->ent_max;
+        P.udesc = L->d_udesc; P.cta_meta = L->d_cta_meta; P.ent_begin = L->d_ent_begin; P.warp_ent = L->d_warp_ent; P.row_owner = L->d_row_owner;
+        P.xbuf_words = L->xbuf_words; P.xrows = L->xrows; P.fabric = fabric;
+        P.xstride = 4LL * L->xbuf_words + 16;      // four rotating buffers + the arrival counter (own line)
+        P.dbg = env_int("MCT_DBG", 0);
+        P.snap_epoch = env_int("MCT_SNAP_EPOCH", 1000);
+        P.spin_limit_cycles = (long long)env_int("MCT_SPIN_LIMIT_MS", 2000) * 2000000LL;
+        if (fabric == 0) break;
+        // Cluster teams: the hardware places a cluster inside one GPC, so only a few clusters of 9..16 CTAs are resident at once
+        // (7 of 16 on a B200: 112 of 148 SMs).  A batch that has more equations than that runs more teams through L2 instead.
         const int maxc = td_sc_max_clusters(P);
-        MCT_REQUIRE(maxc >= 1, MCT_CUDA_ERROR, "thread-block cluster launch not possible for this team size");
-        nteams = std::max(1, std::min(nteams, maxc));
-        P.nteams = nteams;
+        if (maxc >= 1 && (maxc >= nteams_wanted || maxc * L->G * 5 >= h0->n_sm * 4)) { nteams = std::max(1, std::min(nteams, maxc)); P.nteams = nteams; break; }
+        MCT_REQUIRE(maxc >= 1 || L->G > 1, MCT_CUDA_ERROR, "thread-block cluster launch not possible for this team size");
+        fabric = 0;
     }
     if (env_int("MCT_VERBOSE", 0))
         fprintf(stderr, "[mct] Nk=%d sym=%d n_eq=%d: teams=%d x G=%d, U=%d units/warp (%d regs, %d tmem, %d smem, %d L2), rows/CTA<=%d, entries/warp<=%d, smem=%zu B, fabric=%s\n",
@@ -785,7 +867,7 @@ int mct_kernel_destroy(mct_kernel_t h) {
     for (auto &kv : h->slabs) cudaFree(kv.second);
     cudaFree(h->d_scratch); cudaFree(h->d_io);
     for (auto &pe : h->pool) cudaFree(pe.first);
-    if (h->stream) cudaStreamDestroy(h->stream);
+    // (the stream belongs to the device's shared set and stays)
     delete h;
     return MCT_OK;
 }
@@ -1180,7 +1262,7 @@ int mct_equation_shard_prepare(mct_equation_t q, int rank, int world, unsigned c
     MCT_CUDA(cudaSetDevice(q->kernel->device));
     const size_t xwords = grid_lsum_words(q->Nk, q->ns);
     // 4 rotating buffers of task sums + 4 arrival counters (td_grid.cu, phase_lines / phase_scan)
-    if (!q->d_xshard) MCT_CUDA(cudaMalloc(&q->d_xshard, (4 * xwords + 8) * sizeof(double)));
+    if (!q->d_xshard) MCT_CUDA(raw_cuda_malloc((void **)&q->d_xshard, (4 * xwords + 8) * sizeof(double)));     // exported through CUDA IPC: a real allocation
     MCT_CUDA(cudaMemset(q->d_xshard, 0xFF, 4 * xwords * sizeof(double)));          // every slot armed with the sentinel
     MCT_CUDA(cudaMemset(q->d_xshard + 4 * xwords, 0, 8 * sizeof(double)));
     cudaIpcMemHandle_t hd;

@@ -58,12 +58,31 @@ def partition(costs, world, rank):
     return sorted(mine)
 
 
+# measured on B200 at Nk = 500 (profiles/README.md, round 2): a GPU full of small throughput teams finishes 2.3 M kernel
+# evaluations per second in total, each team needs ~5 us per evaluation; one equation alone on a whole-GPU team needs ~3.1 us
+THROUGHPUT_EVALS_PER_S = 2.3e6
+LATENCY_SMALL_TEAM_S = 5.0e-6
+LATENCY_WHOLE_GPU_S = 3.1e-6
+
+
 def outliers(costs, world):
-    """Points too expensive for a throughput team: on `world` ranks a point that alone would take longer on a small team than
-    a rank's fair share of the sweep is solved by a whole-GPU team instead (about 1.5x fewer microseconds per evaluation)."""
+    """Points too expensive for a throughput team: a point that alone on a small team would take longer than the whole
+    sweep's fair share of a rank is solved by a whole-GPU team instead (fewer microseconds per evaluation, but the GPU does
+    nothing else meanwhile).  Only worthwhile when the sweep is spread over several ranks."""
     costs = np.asarray(costs, dtype=np.float64)
-    fair = costs.sum() / world
-    return [int(i) for i in np.argsort(-costs, kind="stable") if costs[i] * 12.0 > fair][:max(1, 2 * world)] if world > 1 else []
+    if world <= 1:
+        return []
+    makespan = costs.sum() / (world * THROUGHPUT_EVALS_PER_S)
+    return [int(i) for i in np.argsort(-costs, kind="stable") if costs[i] * LATENCY_SMALL_TEAM_S > 1.1 * makespan][:world]
+
+
+def weighted_costs(costs, world):
+    """Costs in units of GPU time for the partition: a whole-GPU-team point occupies its GPU alone, i.e. it costs as much as
+    LATENCY_WHOLE_GPU_S * THROUGHPUT_EVALS_PER_S (~7) throughput-team evaluations per evaluation."""
+    w = np.asarray(costs, dtype=np.float64).copy()
+    for i in outliers(costs, world):
+        w[i] *= LATENCY_WHOLE_GPU_S * THROUGHPUT_EVALS_PER_S
+    return w
 
 
 def gather(local_indices, local_values, n_points, world, dist=None):
@@ -128,10 +147,16 @@ def run_sweep(pkg, etas, Nk, device, solver_kwargs=None, batch=None, observable=
         kern = pkg.ModeCouplingKernel(6 * eta / np.pi, 1.0, 1.0, k, Sk, device=device)
         return pkg.MemoryEquation(0.0, 1.0, k ** 2 / Sk, 0.0, Sk, np.zeros(Nk), kern)
 
+    import time
+    timing = run_sweep.last_timing = {"build_equations_s": 0.0, "solve_batch_call_s": 0.0, "release_s": 0.0}
+
     def launch(positions):
         nonlocal ms_tot
+        t0 = time.perf_counter()
         eqs = [equation(etas[i]) for i in positions]
+        t1 = time.perf_counter()
         sols, status, evals, ms = pkg.solve_batch(eqs, pkg.TimeDoublingSolver(**solver_kwargs), download=download)
+        t2 = time.perf_counter()
         if any(status):
             raise pkg.DomainError(f"sweep: solver status {status}")
         for i, s, ev in zip(positions, sols, evals):
@@ -139,6 +164,8 @@ def run_sweep(pkg, etas, Nk, device, solver_kwargs=None, batch=None, observable=
         ms_tot += ms
         for e in eqs:
             e.kernel.close()
+        t3 = time.perf_counter()
+        timing["build_equations_s"] += t1 - t0; timing["solve_batch_call_s"] += t2 - t1; timing["release_s"] += t3 - t2
 
     big = [i for i in big_team if 0 <= i < n]
     for i in big:                                   # a single equation per launch gets the latency geometry (whole GPU)

@@ -36,8 +36,13 @@ def test_cost_model_against_the_measured_table():
     assert np.max(np.abs(model / evals - 1.0)) < 0.25
     assert abs(model.sum() / evals.sum() - 1.0) < 0.03
     big = sweep.outliers(model, 8)
-    assert int(np.argmax(evals)) in big and len(big) <= 16
+    assert int(np.argmax(evals)) in big and len(big) <= 8
     assert sweep.outliers(model, 1) == []
+    w = sweep.weighted_costs(model, 8)
+    parts = [sweep.partition(w, 8, r) for r in range(8)]
+    assert sorted(i for p in parts for i in p) == list(range(512))
+    owner = [r for r in range(8) if big[0] in parts[r]][0]
+    assert w[parts[owner]].sum() <= 1.02 * max(w[big[0]], w.sum() / 8)      # the rank of the critical point gets little else
 
 
 def _worker(rank, world, port, q):
