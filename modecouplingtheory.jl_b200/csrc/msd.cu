@@ -12,42 +12,48 @@ namespace mct {
 
 namespace {
 
-// one block per output time; left-to-right partial sums per thread, fixed-order tree afterwards
-__global__ void msd_table_kernel(const MsdParams P) {
-    __shared__ double red[kWarps];
+// One WARP per output time (8 times in flight per CTA, no block barrier): the lanes walk the wavenumbers with four
+// independent partial sums (four pairs of loads in flight per lane), fixed-order combination, butterfly over the warp.
+// (Round 1 used one block per time with a barrier per time: 2.6 TB/s at config-3 size, see profiles/README.md.)
+__global__ void __launch_bounds__(kThreads) msd_table_kernel(const MsdParams P) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (long it = blockIdx.x; it < P.nt; it += gridDim.x) {
+    const int ns = P.ns, nb = ns * ns, sp = P.s;
+    for (long it = (long)blockIdx.x * kWarps + w; it < P.nt; it += (long)gridDim.x * kWarps) {
         const double *Fs = P.Fs + (size_t)it * P.Nk;
-        double s = 0.0;
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
         if (!P.Cmix) {
             const double *F = P.Fc + (size_t)it * P.Nk;
-            for (int iq = threadIdx.x; iq < P.Nk; iq += blockDim.x) {
-                const double k = P.kvec[iq], c = P.Ck[iq];
-                s += k * k * k * k * (c * c) * F[iq] * Fs[iq];       // :581
+            for (int i0 = lane; i0 < P.Nk; i0 += 128) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int iq = i0 + 32 * j;
+                    if (iq < P.Nk) {
+                        const double k = P.kvec[iq], c = P.Ck[iq];
+                        acc[j] += k * k * k * k * (c * c) * F[iq] * Fs[iq];       // :581
+                    }
+                }
             }
         } else {
             // MSDMultiComponentModeCouplingKernel3D (src/Kernels/MultiComponentKernels.jl:470-486):
             //   K += k^4 C[a,s] C[s,b] F[a,b] Fs  for a, b = 1..Ns,  with  Ns = length(Fs[1])  (:477).
             // Fs[1] is a Float64 there, so the reference's species sum only ever visits a = b = 1 and its golden
             // (test/test_MCMCT.jl:226) is that number: species_terms = 1 reproduces it, species_terms = ns is the documented sum.
-            const int ns = P.ns, nb = ns * ns, sp = P.s;
             const double *F = P.Fc + (size_t)it * P.Nk * nb;
-            for (int iq = threadIdx.x; iq < P.Nk; iq += blockDim.x) {
-                const double k = P.kvec[iq], k4 = k * k * k * k;
-                const double *Fb = F + (size_t)iq * nb, *Cb = P.Cmix + (size_t)iq * nb;
-                for (int a = 0; a < P.species_terms; a++)
-                    for (int b = 0; b < P.species_terms; b++) s += k4 * Cb[a + sp * ns] * Cb[sp + b * ns] * Fb[a + b * ns] * Fs[iq];
+            for (int i0 = lane; i0 < P.Nk; i0 += 128) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int iq = i0 + 32 * j;
+                    if (iq < P.Nk) {
+                        const double k = P.kvec[iq], k4 = k * k * k * k;
+                        const double *Fb = F + (size_t)iq * nb, *Cb = P.Cmix + (size_t)iq * nb;
+                        for (int a = 0; a < P.species_terms; a++)
+                            for (int b = 0; b < P.species_terms; b++) acc[j] += k4 * Cb[a + sp * ns] * Cb[sp + b * ns] * Fb[a + b * ns] * Fs[iq];
+                    }
+                }
             }
         }
-        s = warp_sum(s);
-        if (lane == 0) red[w] = s;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            double t = 0.0;
-            for (int i = 0; i < kWarps; i++) t += red[i];
-            P.Ktab[it] = t * P.scale;                                // :583
-        }
-        __syncthreads();
+        const double s = warp_sum((acc[0] + acc[1]) + (acc[2] + acc[3]));
+        if (lane == 0) P.Ktab[it] = s * P.scale;                                 // :583
     }
 }
 
@@ -191,7 +197,7 @@ int mc_species_weight_launch(const double *F_traj, const double *Cblocks, int Nk
 }
 
 int msd3d_launch(const MsdParams &P, cudaStream_t stream) {
-    const int blocks = (int)std::min<long>(P.nt, 148 * 8);
+    const int blocks = (int)std::min<long>((P.nt + kWarps - 1) / kWarps, 148 * 8);      // one warp per output time
     msd_table_kernel<<<blocks, kThreads, 0, stream>>>(P);
     count_launch();
     MCT_CUDA(cudaGetLastError());
