@@ -43,6 +43,11 @@ size_t td_sc_smem_bytes(const SolveParams &P) { return td_sc_plan_smem(P.Nk, P.G
 
 int td_sc_max_reg_units(int Nk) { return (Nk > 2 * kThreads) ? 2 : 4; }
 
+// which instantiation: -1 = lean (every unit in tensor memory, exchange through L2), otherwise the register-unit count
+static int entry_key(const SolveParams &P) {
+    return (P.UR == 0 && P.US == 0 && P.UT == P.U && P.fabric == 0 && P.G > 1) ? -1 : P.UR;
+}
+
 int td_sc_launch(const SolveParams &P, cudaStream_t stream) {
     const int KPT = (P.Nk + kThreads - 1) / kThreads;
     MCT_REQUIRE(KPT <= kMaxKPT, MCT_UNSUPPORTED, "Nk > 2048 is not supported by the persistent solver");
@@ -50,10 +55,11 @@ int td_sc_launch(const SolveParams &P, cudaStream_t stream) {
     MCT_REQUIRE(P.rows_max <= kThreads, MCT_UNSUPPORTED, "more rows per CTA than threads: use a larger team");
     const size_t smem = td_sc_smem_bytes(P);
     void *fn = nullptr;
-    if (KPT <= 1) fn = td_sc_entry_k1(P.UR);
-    else if (KPT <= 2) fn = td_sc_entry_k2(P.UR);
-    else if (KPT <= 4) fn = td_sc_entry_k4(P.UR);
-    else fn = td_sc_entry_k8(P.UR);
+    const int key = entry_key(P);
+    if (KPT <= 1) fn = td_sc_entry_k1(key);
+    else if (KPT <= 2) fn = td_sc_entry_k2(key);
+    else if (KPT <= 4) fn = td_sc_entry_k4(key);
+    else fn = td_sc_entry_k8(key);
     MCT_REQUIRE(fn != nullptr, MCT_BAD_ARGUMENT, "internal: no kernel instantiation for this UR");
     MCT_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     SolveParams Pc = P;
@@ -86,7 +92,8 @@ namespace mct {
 // how many clusters of G CTAs with this much shared memory can be resident at once (0 if the launch is impossible)
 int td_sc_max_clusters(const SolveParams &P) {
     const int KPT = (P.Nk + kThreads - 1) / kThreads;
-    void *fn = KPT <= 1 ? td_sc_entry_k1(P.UR) : KPT <= 2 ? td_sc_entry_k2(P.UR) : KPT <= 4 ? td_sc_entry_k4(P.UR) : td_sc_entry_k8(P.UR);
+    const int key = entry_key(P);
+    void *fn = KPT <= 1 ? td_sc_entry_k1(key) : KPT <= 2 ? td_sc_entry_k2(key) : KPT <= 4 ? td_sc_entry_k4(key) : td_sc_entry_k8(key);
     if (!fn) return 0;
     const size_t smem = td_sc_smem_bytes(P);
     if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
