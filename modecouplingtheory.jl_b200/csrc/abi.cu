@@ -299,7 +299,7 @@ static Residency choose_residency(const TeamLayout &L, size_t smem_optin, int fa
     // Tensor memory first: a warp owns 256 of the SM's 512 columns in its lane quarter = 10 units of 24 columns, read at
     // ~2.7x the shared-memory rate and without taking registers (scripts/tmem_bench.cu).  Then registers (24 per unit; the
     // instantiations that finish 4 or 8 rows per thread have fewer to spare), then shared memory, the rest streams from L2.
-    const int utmax = env_int("MCT_TMEM", 1) ? std::min(10, env_int("MCT_MAX_TMEM_UNITS", 10)) : 0;
+    const int utmax = env_int("MCT_TMEM", 1) ? std::min(kTmemUnitsPerWarp, env_int("MCT_MAX_TMEM_UNITS", kTmemUnitsPerWarp)) : 0;
     const int urmax = std::min(td_sc_max_reg_units(L.Nk), env_int("MCT_MAX_REG_UNITS", td_sc_max_reg_units(L.Nk)));
     r.UR = 0;
     if (L.U > utmax) for (int ur : {2, 4}) if (ur <= urmax && ur <= L.U) { r.UR = ur; if (ur >= L.U - utmax) break; }
@@ -324,7 +324,7 @@ static int choose_geometry(mct_kernel_t h, int n_eq, TeamLayout **out, int *ntea
     const int g_cap = std::max(1, std::min(n_sm, Nk / 2));               // at least two rows per CTA
     const int g_min = (Nk + kThreads - 1) / kThreads;                    // one owner thread per row
     // on-chip capacity of one CTA in units per warp: tensor memory (10) + registers + what shared memory can hold
-    const int u_tmem = env_int("MCT_TMEM", 1) ? std::min(10, env_int("MCT_MAX_TMEM_UNITS", 10)) : 0;
+    const int u_tmem = env_int("MCT_TMEM", 1) ? std::min(kTmemUnitsPerWarp, env_int("MCT_MAX_TMEM_UNITS", kTmemUnitsPerWarp)) : 0;
     const int u_chip = u_tmem + td_sc_max_reg_units(Nk) + (int)((h->smem_optin - 72 * 1024 - (size_t)48 * Nk) / ((size_t)kWarps * kUV * 32 * 8));
     int G_fit = (int)std::min<long long>(g_cap, std::max<long long>(g_min, (units + (long long)kWarps * u_chip - 1) / ((long long)kWarps * u_chip)));
     int G;

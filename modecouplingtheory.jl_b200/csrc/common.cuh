@@ -28,7 +28,10 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
         }                                           \
     } while (0)
 
-constexpr int kThreads = 256;         // threads per CTA of the persistent solver (8 warps, 1 CTA / SM, up to 255 registers)
+#ifndef MCT_THREADS
+#define MCT_THREADS 256
+#endif
+constexpr int kThreads = MCT_THREADS; // threads per CTA of the persistent solver (1 CTA / SM)
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxKPT = 8;            // wavenumbers per thread in the redundant update phase -> Nk <= 2048
 constexpr int kFlagStride = 16;       // one 128-byte line per team-barrier flag (unsigned long long units)

@@ -41,7 +41,7 @@ SmemOffsets td_sc_plan_smem(int Nk, int G, int rows_max, int ent_max, int lane_c
 
 size_t td_sc_smem_bytes(const SolveParams &P) { return td_sc_plan_smem(P.Nk, P.G, P.rows_max, P.ent_max, P.lane_cap, P.U, P.US, P.fabric, P.xbuf_words).total; }
 
-int td_sc_max_reg_units(int Nk) { return (Nk > 2 * kThreads) ? 2 : 4; }
+int td_sc_max_reg_units(int Nk) { return kThreads > 256 ? 0 : ((Nk > 2 * kThreads) ? 2 : 4); }
 
 // which instantiation: -1 = lean (every unit in tensor memory, exchange through L2), otherwise the register-unit count
 static int entry_key(const SolveParams &P) {

@@ -63,6 +63,8 @@ size_t td_sc_smem_bytes(const SolveParams &P);
 // largest UR worth using at this Nk (24 registers per register-resident unit; the instantiations that finish 4 or 8 rows
 // per thread have fewer registers to spare)
 int td_sc_max_reg_units(int Nk);
+// units of a warp that fit its share of tensor memory (512 columns per lane quarter, shared by the warps w, w+4, ...)
+constexpr int kTmemUnitsPerWarp = (512 / ((kWarps + 3) / 4)) / (2 * kUV);
 int td_sc_launch(const SolveParams &P, cudaStream_t stream);
 int td_sc_max_clusters(const SolveParams &P);
 

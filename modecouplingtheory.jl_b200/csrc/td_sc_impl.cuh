@@ -91,6 +91,7 @@ __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 constexpr int kTmemCols = 512;                    // the whole tensor memory of the SM (one CTA per SM)
 constexpr int kTmemUnitCols = 2 * kUV;            // 24 columns of 32 bits = 12 doubles per lane
+constexpr int kTmemColsPerWarp = kTmemCols / ((kWarps + 3) / 4);      // the warps w, w+4, ... share a lane quarter
 
 #ifdef MCT_PROFILE
 #define PROF(i) do { long long now__ = clock64(); prof[i] += now__ - tlast; tlast = now__; } while (0)
@@ -921,7 +922,7 @@ __global__ void __launch_bounds__(kThreads, 1) td_sc_kernel(const SolveParams P)
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        T.tbase = *(volatile unsigned *)slot + ((unsigned)(32 * (T.warp & 3)) << 16) + (unsigned)((T.warp >> 2) * (kTmemCols / 2));
+        T.tbase = *(volatile unsigned *)slot + ((unsigned)(32 * (T.warp & 3)) << 16) + (unsigned)((T.warp >> 2) * kTmemColsPerWarp);
     }
     __syncthreads();
     if (P.fabric == 1) cluster_sync_all();        // nobody stores into a peer before its buffers are armed
