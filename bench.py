@@ -50,8 +50,8 @@ NK = 1000
 ETA = 0.5155
 WORKLOAD = ("config3: hard-sphere MCT, Percus-Yevick S(k), Nk=1000, eta=0.5155 (near eta_c), overdamped, "
             "TimeDoublingSolver(N=32, dt=1e-10, t_max=1e10, tol=1e-10)")
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 34611712 + 26191872      # dram__bytes_read.sum + dram__bytes_write.sum of one launch
-NCU_TRAFFIC_SOURCE = "profiles/ncu_full_r01_td_sc_kernel.csv"
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 30113536 + 25608448      # dram__bytes_read.sum + dram__bytes_write.sum of one launch
+NCU_TRAFFIC_SOURCE = "profiles/ncu_full_r02_td_sc_kernel.csv"
 METRIC = "hs_mct_nk1000_kernel_evals_per_s"
 UNIT = "kernel evals/s"
 
