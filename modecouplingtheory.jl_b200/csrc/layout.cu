@@ -133,13 +133,9 @@ long long range_units(int Nk, int sym, int r0, int r1) {
     for (int d0 = r0; d0 < r1; d0 += kRB) n += block_unit_count(Nk, sym, d0, r1);
     return n;
 }
-// time a CTA spends on a range: every unit costs its operand loads (~2 row-equivalents) plus one product and three
-// FMAs per row that exists (a trailing block with fewer than 4 rows skips the arithmetic of the missing rows)
-long long range_cost(int Nk, int sym, int r0, int r1) {
-    long long n = 0;
-    for (int d0 = r0; d0 < r1; d0 += kRB) n += (long long)block_unit_count(Nk, sym, d0, r1) * (2 + std::min(kRB, r1 - d0));
-    return n;
-}
+// time a CTA spends on a range: its number of units (since round 2 every unit costs the same: rows that do not exist in a
+// trailing block are no longer skipped, their table values are zero)
+long long range_cost(int Nk, int sym, int r0, int r1) { return range_units(Nk, sym, r0, r1); }
 
 void partition_rows(int Nk, int G, int sym, std::vector<int> &row0) {
     auto fits = [&](long long cap, std::vector<int> *out) {
