@@ -280,6 +280,26 @@ def kshard_record(args, pkg, torch, dist, rank, world, dev):
         same = torch.tensor([1.0 if (evalsN == evals1 and np.array_equal(FN, F1)) else 0.0], dtype=torch.float64, device=f"cuda:{dev}")
         dist.all_reduce(same, op=dist.ReduceOp.MIN)
         sharded.close()
+        # the collective the north star names for this step, for comparison: NCCL all-gather of F(k) (dof doubles in total) plus
+        # a MAX all-reduce of the 8-byte error word, launched from the host once per fixed-point iteration (what a solver that
+        # is NOT resident on the device would pay per evaluation besides its kernels); CUDA events, max over ranks
+        dof = kern.dof
+        shard = torch.zeros((dof + world - 1) // world, dtype=torch.float64, device=f"cuda:{dev}")
+        full = torch.zeros(shard.numel() * world, dtype=torch.float64, device=f"cuda:{dev}")
+        err = torch.zeros(1, dtype=torch.float64, device=f"cuda:{dev}")
+        for _ in range(20):
+            dist.all_gather_into_tensor(full, shard); dist.all_reduce(err, op=dist.ReduceOp.MAX)
+        torch.cuda.synchronize(); dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 200
+        e0.record()
+        for _ in range(reps):
+            dist.all_gather_into_tensor(full, shard); dist.all_reduce(err, op=dist.ReduceOp.MAX)
+        e1.record(); torch.cuda.synchronize()
+        nccl_us = torch.tensor([1e3 * e0.elapsed_time(e1) / reps], dtype=torch.float64, device=f"cuda:{dev}")
+        dist.all_reduce(nccl_us, op=dist.ReduceOp.MAX)
+        rec.update({"nccl_allgather_plus_maxreduce_us_per_iteration": nccl_us.item(), "us_per_evaluation_sharded": 1e3 * msN / evalsN,
+                    "us_per_evaluation_single_gpu": 1e3 * ms1 / evals1})
         rec.update({"evals_per_s": evalsN / (msN * 1e-3), "ms": msN, "speedup_over_single_gpu": ms1 / msN,
                     "bitwise_equal_to_single_gpu": bool(same.item() == 1.0),
                     "exchange": "device-initiated pull of the line sums from CUDA-IPC-mapped peer buffers over NVLink (no collective call)"})
