@@ -332,9 +332,11 @@ static int choose_geometry(mct_kernel_t h, int n_eq, TeamLayout **out, int *ntea
         // latency: as many CTAs as keep every warp busy with a couple of units per iteration
         const int target = env_int("MCT_TARGET_UNITS", 2);
         G = (int)std::min<long long>(g_cap, std::max<long long>(G_fit, (units + (long long)kWarps * target - 1) / ((long long)kWarps * target)));
-        // small problems: a team of up to 16 CTAs is a thread-block cluster (DSMEM exchange, ~3x cheaper than through L2),
-        // so spread down to one unit per warp
-        if (G <= 16 && env_int("MCT_CLUSTER", 1)) G = (int)std::min<long long>(std::min(16, g_cap), std::max<long long>(G, (units + kWarps - 1) / kWarps));
+        // small problems: spread to at least 32 CTAs (one unit or less per warp) on the L2 fabric.  Round 1 used a thread-block
+        // cluster of <= 16 CTAs with a DSMEM exchange here; since the round-2 rebuild of the L2 exchange the larger L2 team is
+        // faster (Nk=100: 3.4 us per evaluation at G=37, 3.6 at a cluster of 16, 4.0 at a cluster of 11) -- the cluster fabric
+        // remains for explicitly requested team sizes (MCT_TEAM_SIZE <= 16).
+        G = (int)std::min<long long>(g_cap, std::max<long long>(G, env_int("MCT_MIN_LATENCY_TEAM", 32)));
     } else {
         // throughput: the smallest team whose tables stay on chip (the exchange is a per-CTA cost)
         G = G_fit;
