@@ -472,6 +472,12 @@ static int run_batch(int n, mct_equation_t *eqs, int mode, double tol, long long
         P.rows_max = L->rows_max; P.rb_max = L->rb_max; P.ent_max = L->ent_max;
         P.udesc = L->d_udesc; P.cta_meta = L->d_cta_meta; P.ent_begin = L->d_ent_begin; P.warp_ent = L->d_warp_ent; P.row_owner = L->d_row_owner;
         P.xbuf_words = L->xbuf_words; P.xrows = L->xrows; P.fabric = fabric;
+        // history rings in shared memory when they fit beside everything else (time-doubling solves only)
+        P.ring_smem = 0;
+        if (mode == 0 && env_int("MCT_RING_SMEM", 1)) {
+            P.ring_smem = 1;
+            if (td_sc_smem_bytes(P) + 1024 > h0->smem_optin) P.ring_smem = 0;
+        }
         P.xstride = 4LL * L->xbuf_words + 16;      // four rotating buffers + the arrival counter (own line)
         P.dbg = env_int("MCT_DBG", 0);
         P.snap_epoch = env_int("MCT_SNAP_EPOCH", 1000);

@@ -10,7 +10,7 @@ void *td_sc_entry_k1(int UR);
 void *td_sc_entry_k2(int UR);
 void *td_sc_entry_k4(int UR);
 void *td_sc_entry_k8(int UR);
-SmemOffsets td_sc_plan_smem(int Nk, int G, int rows_max, int ent_max, int lane_cap, int U, int US, int fabric, int xbuf_words) {
+SmemOffsets td_sc_plan_smem(int Nk, int G, int rows_max, int ent_max, int lane_cap, int U, int US, int fabric, int xbuf_words, int ring_doubles) {
     SmemOffsets p;
     size_t o = 0;
     const int NkP = even_up(Nk), NkF = even_up(Nk + 2 * kFPad);
@@ -34,12 +34,17 @@ SmemOffsets td_sc_plan_smem(int Nk, int G, int rows_max, int ent_max, int lane_c
     p.desc = (unsigned)o; o += (size_t)kWarps * (U + 2) * 8;        // operand addresses of every unit (int2)
     o = (o + 15) & ~(size_t)15;
     p.tab = (unsigned)o; o += (size_t)kWarps * US * kUV * 32 * 8;
+    p.ring = ring_doubles > 0 ? (unsigned)o : 0u; o += (size_t)ring_doubles * 8;
     p.total = (unsigned)o;
     return p;
 }
 
 
-size_t td_sc_smem_bytes(const SolveParams &P) { return td_sc_plan_smem(P.Nk, P.G, P.rows_max, P.ent_max, P.lane_cap, P.U, P.US, P.fabric, P.xbuf_words).total; }
+// doubles of the shared-memory history rings: F_temp, K_temp, F_I, K_I of the owned rows, 4N slots each, rows padded by one
+// word against bank conflicts
+int td_sc_ring_doubles(const SolveParams &P) { return P.ring_smem ? 4 * even_up(P.rows_max) * (4 * P.N + 1) : 0; }
+
+size_t td_sc_smem_bytes(const SolveParams &P) { return td_sc_plan_smem(P.Nk, P.G, P.rows_max, P.ent_max, P.lane_cap, P.U, P.US, P.fabric, P.xbuf_words, td_sc_ring_doubles(P)).total; }
 
 int td_sc_max_reg_units(int Nk) { return kThreads > 256 ? 0 : ((Nk > 2 * kThreads) ? 2 : 4); }
 
@@ -63,7 +68,7 @@ int td_sc_launch(const SolveParams &P, cudaStream_t stream) {
     MCT_REQUIRE(fn != nullptr, MCT_BAD_ARGUMENT, "internal: no kernel instantiation for this UR");
     MCT_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     SolveParams Pc = P;
-    Pc.so = td_sc_plan_smem(P.Nk, P.G, P.rows_max, P.ent_max, P.lane_cap, P.U, P.US, P.fabric, P.xbuf_words);
+    Pc.so = td_sc_plan_smem(P.Nk, P.G, P.rows_max, P.ent_max, P.lane_cap, P.U, P.US, P.fabric, P.xbuf_words, td_sc_ring_doubles(P));
     void *args[] = {(void *)&Pc};
     dim3 grid(P.nteams * P.G), block(kThreads);
     if (P.fabric == 1) {

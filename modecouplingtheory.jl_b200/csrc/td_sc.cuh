@@ -22,7 +22,7 @@ struct EqDev {
 // byte offsets of the kernel's arrays inside its dynamic shared memory (filled by td_sc_launch; kept in the
 // parameter bank so that they cost no registers)
 struct SmemOffsets {
-    unsigned F1, F2, rho, off, wt, own, part, lane, C, X, scan, misc, eq, xd, desc, tab, total;
+    unsigned F1, F2, rho, off, wt, own, part, lane, C, X, scan, misc, eq, xd, desc, tab, ring, total;
 };
 
 struct SolveParams {
@@ -35,6 +35,7 @@ struct SolveParams {
     int UT;                     // units per warp resident in tensor memory (24 of the warp's 256 columns each, <= 10)
     int US;                     // units per warp resident in shared memory; the remaining U-UR-UT-US stream from L2
     int rows_max, rb_max, ent_max, lane_cap;
+    int ring_smem;              // 1: the history rings of the owned rows live in shared memory ([4][rows_max][4N+1]), 0: in global memory
     const int *udesc, *cta_meta, *ent_begin, *warp_ent, *row_owner;
     // team communication
     double *xbuf;               // [nteams][4][xbuf_words]: rotating exchange buffers of self-validating 8-byte slots
@@ -60,6 +61,7 @@ __host__ __device__ inline int even_up(int n) { return (n + 1) & ~1; }
 
 // shared memory needed by a launch with these parameters; US = 0 gives the fixed part
 size_t td_sc_smem_bytes(const SolveParams &P);
+int td_sc_ring_doubles(const SolveParams &P);
 // largest UR worth using at this Nk (24 registers per register-resident unit; the instantiations that finish 4 or 8 rows
 // per thread have fewer registers to spare)
 int td_sc_max_reg_units(int Nk);

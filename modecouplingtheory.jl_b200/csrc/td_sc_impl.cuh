@@ -629,7 +629,11 @@ struct Team {
     __device__ __forceinline__ void solve_one(const EqDev &E) {
         const int N = P.N, n4 = 4 * N, n2 = 2 * N;
         enum { Ft = 0, Kt = 1, FI = 2, KI = 3 };          // F_temp, K_temp, F_I, K_I  (src/TimeDoublingSolver.jl:3-18)
-#define RING(R, k, s) E.ring[((size_t)(R) * P.Nk + (k)) * n4 + ((s) - 1)]   /* slot s is 1-based as in the reference */
+        // history rings of the owned rows: in shared memory when they fit (the memory convolution of a step reads ~2 x 4N slots
+        // per row; from the L2-resident global rings that is a chain of ~700-cycle loads), else in global memory
+        double *const rbase = P.ring_smem ? (double *)(smem_raw + P.so.ring) : E.ring;
+        const int rrows = P.ring_smem ? even_up(P.rows_max) : P.Nk, rk0 = P.ring_smem ? row0 : 0, rn = P.ring_smem ? n4 + 1 : n4;
+#define RING(R, k, s) rbase[((size_t)(R) * rrows + ((k) - rk0)) * rn + ((s) - 1)]   /* slot s is 1-based as in the reference */
         oF1 = (E.Fc_traj != nullptr) ? P.so.F1 : P.so.F2;        // tagged kernels: A = V * Fc[iq] * Fs[ip]
         load_tables(E);
         load_own(E);
