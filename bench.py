@@ -167,10 +167,11 @@ def run_reference(args, rank):
             vals.append(v)
     value = float(np.mean(vals))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": args.warmup, "ms_per_step": 1e3 * 200.0 / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic (analytic Percus-Yevick hard-sphere S(k))",
-            "config": {"workload": WORKLOAD, "note": "reference = ModeCouplingTheory.jl (Julia, not installable here: no julia binary, "
-                       "no network); timed instead: oracle/mct_oracle.c, the C restatement in the reference's operation order"},
+            "config": {"workload": WORKLOAD},
+            "details": {"note": "reference = ModeCouplingTheory.jl (Julia, not installable here: no julia binary, no network); timed "
+                                "instead: oracle/mct_oracle.c, the C restatement in the reference's operation order"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample +
                              "; 1 thread because the reference hot path is single-threaded (@turbo, no @threads)",
                              "spread": {"min": float(np.min(vals)), "max": float(np.max(vals)), "samples": len(vals)}},
@@ -467,9 +468,9 @@ def main():
             "metric": METRIC, "value": evals_all / (ms_max * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic (analytic Percus-Yevick hard-sphere S(k))",
-            "config": {"workload": WORKLOAD, "kernel_evals_per_solve": evals_per_solve, "output_times": nt,
-                       "solve_wall_ms_device": launch_ms, "l2": "256 MiB buffer written between timed iterations (L2 flush)",
-                       "sharding": "one independent equation per GPU, no data-path collective" if world > 1 else "single GPU"},
+            "config": {"workload": WORKLOAD, "l2": "256 MiB buffer written between timed iterations (L2 flush)"},
+            "details": {"kernel_evals_per_solve": evals_per_solve, "output_times": nt, "solve_wall_ms_device": launch_ms,
+                        "sharding": "one independent equation per GPU, no data-path collective" if world > 1 else "single GPU"},
             "e2e": {"value": e2e_evals_all / e2e_max, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "solve_wall_ms": 1e3 * e2e_max / args.steps},
             "gpu_launches": int(launches_all),
