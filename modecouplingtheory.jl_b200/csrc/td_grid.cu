@@ -12,8 +12,8 @@
 //     sum(term1) = F_q .* G1_p,   sum(term2) = G3_q .* G2_p,   sum(term3) = G2_q .* G3_p,   sum(term4) = G1_q .* F_p
 // so an entry A_m[a,b,iq,ip] costs O(1) per (a,b) and A is never stored: a warp owns one diagonal / antidiagonal of
 // the (iq, ip) plane and accumulates its 3 Ns^2 line sums; bengtzelius3! (:2-43) then is a prefix over the lines.
-// This first version is throughput-naive (operands re-read from L2 per entry, sequential prefix); it exists for
-// parity and coverage, the tuned path is the single-component one.
+// Per evaluation the grid passes three cg grid barriers (2.1 us each at 148 CTAs -- profiles/gridsync_bench_r02.txt; a
+// hand-rolled counter barrier measures 1.7 us, i.e. ~1 % of a config-4 evaluation, so cg's is kept).
 #include <cooperative_groups.h>
 
 #include "td_grid.cuh"
@@ -220,37 +220,60 @@ struct Ctx {
     //      FP64 instructions per entry (10 and 28 when every entry is walked on its own), which is what bounds this phase.
     //      The 21 partial sums of a task are written per task; phase_scan adds the (at most two) tasks of a line.
     //      Tasks are dealt to warps longest first in snake order; rank r of a k-sharded solve takes every world-th task.
+    // One half (two consecutive wavenumbers) of a chunk's staged operands: F k, G1 k, G2 k, G3 k and k^2.  The staging
+    // multiplies the four vectors by k so that a product of a q-side and a p-side operand carries the weight pq.
+    struct Half { double2 F, g1, g2, g3, k2; };
+    static __device__ __forceinline__ double el(const double2 &v, int i) { return i ? v.y : v.x; }
+    static __device__ __forceinline__ void halve(Half &h) {
+        h.F.x *= 0.5; h.F.y *= 0.5; h.g1.x *= 0.5; h.g1.y *= 0.5; h.g2.x *= 0.5; h.g2.y *= 0.5; h.g3.x *= 0.5; h.g3.y *= 0.5;
+    }
+    // entries (A0 + a, B0 + b), a, b in {0, 1}, of a tile: 12 FP64 instructions each
+    template <bool DIAG, int A0, int B0>
+    static __device__ __forceinline__ void quarter(const Half &x, const Half &y, double (&acc)[3][8]) {
+#pragma unroll
+        for (int a = 0; a < 2; a++)
+#pragma unroll
+            for (int b = 0; b < 2; b++) {
+                const int idx = DIAG ? (B0 + b) - (A0 + a) + 3 : (A0 + a) + (B0 + b);
+                // with P = pq: t1 = P F_q G1_p, t2 = P G2_p G3_q, t3 = P G2_q G3_p, t4 = P G1_q F_p; d = p^2 - q^2
+                const double t4 = el(x.g1, a) * el(y.F, b), t3 = el(x.g2, a) * el(y.g3, b);
+                const double v = fma(el(x.F, a), el(y.g1, b), t4), dm = fma(el(x.F, a), el(y.g1, b), -t4);
+                const double u = fma(el(y.g2, b), el(x.g3, a), t3);
+                const double d = el(y.k2, b) - el(x.k2, a), c = v - u;
+                acc[0][idx] += v + u;                              // :186-192 (V1: pq, V2: pq(p^2-q^2)^2, V3: 2pq(p^2-q^2))
+                acc[1][idx] = fma(c * d, d, acc[1][idx]);
+                acc[2][idx] = fma(dm, d, acc[2][idx]);
+            }
+    }
+    // Walk of the tiles I = lo + lane, lo + lane + 32, ... < hi of a tile diagonal (J = I + off) or antidiagonal (J = off - I).
+    // The tile `mid` (middle of an antidiagonal, which holds both members of its mirror pairs) enters with half weight
+    // because the caller doubles the sums afterwards.  Measured and dropped (profiles/README.md, round 2): loading the
+    // next tile's operands into the registers of the current one as its halves die, pinned with warp fences, and forcing
+    // the first use of every load group before the next group is issued -- ptxas' own placement (all 20 loads next to
+    // their first use) is 5 % faster, the two warps of an SM partition hide each other's load latency.
     template <bool DIAG>
-    __device__ __forceinline__ void tile_walk(const double *sm, int gs, int lo, int hi, int off, double (&acc)[3][8]) {
+    __device__ __forceinline__ void tile_walk(const double *sm, int gs, int lo, int hi, int off, int mid, double (&acc)[3][8]) {
         const double *sF = sm, *s1 = sm + gs, *s2 = sm + 2 * gs, *s3 = sm + 3 * gs, *sk = sm + 4 * gs;
         // the 4 operands of chunk I live in the 16-byte slots 2I and 2I+1, exchanged when bit 2 of I is set (swz): the 8
         // lanes of a quarter warp then hit 8 different bank groups instead of 4 twice
-        auto ld4 = [](const double *p, int o0, int o1, double (&v)[4]) {
-            const double2 u = *reinterpret_cast<const double2 *>(p + o0), w = *reinterpret_cast<const double2 *>(p + o1);
-            v[0] = u.x; v[1] = u.y; v[2] = w.x; v[3] = w.y;
+        auto ldh = [&](int chunk, int h) {
+            const int o = 4 * chunk + 2 * (h ^ ((chunk >> 2) & 1));
+            Half r;
+            r.F = *reinterpret_cast<const double2 *>(sF + o); r.g1 = *reinterpret_cast<const double2 *>(s1 + o);
+            r.g2 = *reinterpret_cast<const double2 *>(s2 + o); r.g3 = *reinterpret_cast<const double2 *>(s3 + o);
+            r.k2 = *reinterpret_cast<const double2 *>(sk + o);
+            return r;
         };
-        for (int I = lo + lane; I < hi; I += 32) {
+        int I = lo + lane;
+        for (; I < hi; I += 32) {
             const int J = DIAG ? I + off : off - I;
-            const int sx = (I >> 2) & 1, sy = (J >> 2) & 1;
-            const int x0 = 4 * I + 2 * sx, x1 = 4 * I + 2 - 2 * sx, y0 = 4 * J + 2 * sy, y1o = 4 * J + 2 - 2 * sy;
-            double xF[4], x1v[4], x2[4], x3[4], xk[4], yF[4], y1[4], y2[4], y3[4], yk[4], xq[4], yp[4];
-            ld4(sF, x0, x1, xF); ld4(s1, x0, x1, x1v); ld4(s2, x0, x1, x2); ld4(s3, x0, x1, x3); ld4(sk, x0, x1, xk);
-            ld4(sF, y0, y1o, yF); ld4(s1, y0, y1o, y1); ld4(s2, y0, y1o, y2); ld4(s3, y0, y1o, y3); ld4(sk, y0, y1o, yk);
-#pragma unroll
-            for (int i = 0; i < 4; i++) { xq[i] = xk[i] * xk[i]; yp[i] = yk[i] * yk[i]; }
-#pragma unroll
-            for (int a = 0; a < 4; a++)
-#pragma unroll
-                for (int b = 0; b < 4; b++) {
-                    const int idx = DIAG ? b - a + 3 : a + b;
-                    const double pq2 = yp[b] - xq[a], P1 = yk[b] * xk[a], w = P1 * pq2, P2 = w * pq2;   // p = k[ip], q = k[iq]
-                    // t1 = F_q G1_p, t2 = G2_p G3_q, t3 = G2_q G3_p, t4 = G1_q F_p; only t1 +- t4 and t2 + t3 are needed
-                    const double t4 = x1v[a] * yF[b], t3 = x2[a] * y3[b];
-                    const double v = fma(xF[a], y1[b], t4), dm = fma(xF[a], y1[b], -t4), u = fma(y2[b], x3[a], t3);
-                    acc[0][idx] = fma(v + u, P1, acc[0][idx]);       // :186-192 (V1: pq, V2: pq(p^2-q^2)^2, V3: 2pq(p^2-q^2))
-                    acc[1][idx] = fma(v - u, P2, acc[1][idx]);
-                    acc[2][idx] = fma(dm, w, acc[2][idx]);
-                }
+            Half x0 = ldh(I, 0), x1 = ldh(I, 1);
+            const Half y0 = ldh(J, 0), y1 = ldh(J, 1);
+            if (!DIAG && __builtin_expect(I == mid, 0)) { halve(x0); halve(x1); }
+            quarter<DIAG, 0, 0>(x0, y0, acc);
+            quarter<DIAG, 0, 2>(x0, y1, acc);
+            quarter<DIAG, 2, 0>(x1, y0, acc);
+            quarter<DIAG, 2, 2>(x1, y1, acc);
         }
     }
     __device__ void phase_lines() {
@@ -265,13 +288,17 @@ struct Ctx {
         for (int i = threadIdx.x; i < gs; i += blockDim.x) {
             const bool in = i < Nk;
             const int c = i >> 1, ph = ((c ^ ((c >> 3) & 1)) << 1) | (i & 1);      // swz: see tile_walk
+            const double kq = in ? P.kvec[i] : 0.0;
 #pragma unroll
-            for (int j = 0; j < 4; j++) gsm[j * gs + ph] = in ? P.G[(size_t)j * dof + (size_t)e * Nk + i] : 0.0;
-            gsm[4 * gs + ph] = in ? P.kvec[i] : 0.0;
+            for (int j = 0; j < 4; j++) gsm[j * gs + ph] = in ? P.G[(size_t)j * dof + (size_t)e * Nk + i] * kq : 0.0;
+            gsm[4 * gs + ph] = kq * kq;
         }
         __syncthreads();
         const double pab = P.pref[e];
-        const int wpb = blockDim.x >> 5, wi = chunk * wpb + (threadIdx.x >> 5), wstride = nchunk * wpb;
+        // the two warps of an SM partition (w and w + 4) take complementary positions of the dealing order, so that every
+        // partition carries the same work (tasks are dealt longest first in snake order)
+        const int wpb = blockDim.x >> 5, hw = wpb >> 1, w = threadIdx.x >> 5, wstride = nchunk * wpb;
+        const int wi = w < hw ? chunk * hw + w : wstride - 1 - (chunk * hw + w - hw);
         for (int round = 0;; round++) {
             const int slot = round * wstride + ((round & 1) ? wstride - 1 - wi : wi);
             const int t = slot * world + (rank + slot) % world;   // position in the longest-first order; the rotation gives
@@ -287,17 +314,16 @@ struct Ctx {
                 for (int i = 0; i < 8; i++) acc[m][i] = 0.0;
             int task;
             if (kind == 1) {
-                // the mirror argument holds along an antidiagonal too: tiles I < J count twice, the middle tile (S even)
-                // holds both members of its pairs already
+                // the mirror argument holds along an antidiagonal too: tiles I < J count twice; the middle tile (S even)
+                // holds both members of its pairs already and is walked with half weight
                 const int S = nc - lam - 1; task = nc + S;
-                tile_walk<false>(gsm, gs, 0, (S + 1) >> 1, S, acc);
+                tile_walk<false>(gsm, gs, 0, (S >> 1) + 1, S, (S & 1) ? -1 : (S >> 1), acc);
 #pragma unroll
                 for (int m = 0; m < 3; m++)
 #pragma unroll
                     for (int i = 0; i < 7; i++) acc[m][i] += acc[m][i];
-                if (!(S & 1)) tile_walk<false>(gsm, gs, (S >> 1) - lane, (S >> 1) + 1 - lane, S, acc);     // lane 0 alone
             }
-            else { task = lam; tile_walk<true>(gsm, gs, 0, nc - lam, lam, acc); }
+            else { task = lam; tile_walk<true>(gsm, gs, 0, nc - lam, lam, -1, acc); }
             // 24 values (3 x 7 used) summed over the 32 lanes by halving: lanes exchange the half they do not keep
             double v12[12], v6[6], v4[4], v2[2];
             {
