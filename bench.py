@@ -268,7 +268,7 @@ def kshard_record(args, pkg, torch, dist, rank, world, dev):
                        f"Newtonian, TimeDoublingSolver(N=4, dt=1e-4, t_max={args.mc_tmax}, tol=1e-10)",
            "n_gpus": world, "scaling": "strong", "kernel_evals": int(evals1),
            "single_gpu_evals_per_s": evals1 / (ms1 * 1e-3), "single_gpu_ms": ms1,
-           "fp64_ginstr_per_s_single_gpu": 14.0 * ns * ns * Nk * Nk * 0.75 * evals1 / (ms1 * 1e-3) / 1e9, "fp64_peak_ginstr_per_s": 17700.0}
+           "fp64_ginstr_per_s_single_gpu": 12.0 * ns * ns * Nk * Nk * 0.75 * evals1 / (ms1 * 1e-3) / 1e9, "fp64_peak_ginstr_per_s": 17700.0}
     if world > 1:
         def all_gather(b):
             out = [None] * world

@@ -12,8 +12,9 @@
 //     sum(term1) = F_q .* G1_p,   sum(term2) = G3_q .* G2_p,   sum(term3) = G2_q .* G3_p,   sum(term4) = G1_q .* F_p
 // so an entry A_m[a,b,iq,ip] costs O(1) per (a,b) and A is never stored: a warp owns one diagonal / antidiagonal of
 // the (iq, ip) plane and accumulates its 3 Ns^2 line sums; bengtzelius3! (:2-43) then is a prefix over the lines.
-// Per evaluation the grid passes three cg grid barriers (2.1 us each at 148 CTAs -- profiles/gridsync_bench_r02.txt; a
-// hand-rolled counter barrier measures 1.7 us, i.e. ~1 % of a config-4 evaluation, so cg's is kept).
+// Per evaluation the grid passes three cg grid barriers (2.1 us each at 148 CTAs -- profiles/gridsync_bench_r02.txt).  A
+// hand-rolled arrival-counter barrier measures 1.7 us alone but changed nothing inside the solver (81.4 against 81.0 us per
+// config-4 evaluation: the wait is the arrival skew of the blocks, not the barrier), so cg's is kept.
 #include <cooperative_groups.h>
 
 #include "td_grid.cuh"
@@ -216,8 +217,8 @@ struct Ctx {
     //      is walked: for a fixed species pair the entry at (ip, iq) equals the one at (iq, ip) (t1 <-> t4, t2 <-> t3 and
     //      the sign of p^2 - q^2 swap together), so the line sums of d and -d are the same number, and an antidiagonal
     //      is twice its half with iq < ip (plus the middle entry).  A lane keeps
-    //      the 2 x 4 x 5 operands of a tile and 3 x 7 line accumulators in registers: 2.5 shared-memory words and 14
-    //      FP64 instructions per entry (10 and 28 when every entry is walked on its own), which is what bounds this phase.
+    //      the 2 x 4 x 5 operands of a tile and 3 x 7 line accumulators in registers: 2.5 shared-memory words and 12
+    //      FP64 instructions per entry, which is what bounds this phase.
     //      The 21 partial sums of a task are written per task; phase_scan adds the (at most two) tasks of a line.
     //      Tasks are dealt to warps longest first in snake order; rank r of a k-sharded solve takes every world-th task.
     // One half (two consecutive wavenumbers) of a chunk's staged operands: F k, G1 k, G2 k, G3 k and k^2.  The staging
