@@ -457,9 +457,10 @@ OK_API void ok_kernel_eval(ok_kernel *K, const double *F, long t_index, double *
     int Nk = K->Nk, ns = K->ns;
     switch (K->type) {
     case OK_SC3D: {
-        /* fill_A! :190-208 */
-        for (int iq = 0; iq < Nk; iq++)
-            for (int ip = 0; ip < Nk; ip++) {
+        /* fill_A! :190-208.  The reference's loop nest is under @turbo (LoopVectorization picks the order and vectorises
+         * along the contiguous index iq); the element-wise products do not depend on the order, so iq is the inner loop */
+        for (int ip = 0; ip < Nk; ip++)
+            for (int iq = 0; iq < Nk; iq++) {
                 double f4 = F[ip] * F[iq];
                 size_t ix = (size_t)iq + (size_t)ip * Nk;
                 K->A1[ix] = K->V1[ix] * f4; K->A2[ix] = K->V2[ix] * f4; K->A3[ix] = K->V3[ix] * f4;
@@ -470,8 +471,8 @@ OK_API void ok_kernel_eval(ok_kernel *K, const double *F, long t_index, double *
     case OK_TAGGED3D: {
         /* fill_A!(kernel,F,t) :428-448 */
         const double *Fc = K->Fc + (size_t)t_index * Nk;
-        for (int iq = 0; iq < Nk; iq++)
-            for (int ip = 0; ip < Nk; ip++) {
+        for (int ip = 0; ip < Nk; ip++)
+            for (int iq = 0; iq < Nk; iq++) {
                 double f4 = F[ip] * Fc[iq];
                 size_t ix = (size_t)iq + (size_t)ip * Nk;
                 K->A1[ix] = K->V1[ix] * f4; K->A2[ix] = K->V2[ix] * f4; K->A3[ix] = K->V3[ix] * f4;
@@ -483,8 +484,8 @@ OK_API void ok_kernel_eval(ok_kernel *K, const double *F, long t_index, double *
         /* fill_A! MultiComponentKernels.jl:335-370 */
         int nc = K->ncs; size_t nb = (size_t)nc * nc; int s0 = K->s;
         const double *Fc = K->Fc + (size_t)t_index * Nk * nb;
-        for (int iq = 0; iq < Nk; iq++)
-            for (int ip = 0; ip < Nk; ip++) {
+        for (int ip = 0; ip < Nk; ip++)
+            for (int iq = 0; iq < Nk; iq++) {
                 double fp = F[ip], a1 = 0.0, a2 = 0.0, a3 = 0.0;
                 size_t ix = (size_t)iq + (size_t)ip * Nk;
                 for (int a = 0; a < nc; a++)
