@@ -246,7 +246,8 @@ struct Ctx {
                 acc[2][idx] = fma(dm, d, acc[2][idx]);
             }
     }
-    // Walk of the tiles I = lo + lane, lo + lane + 32, ... < hi of a tile diagonal (J = I + off) or antidiagonal (J = off - I).
+    // Walk of the tiles I = lo + l, lo + l + 16, ... < hi (l = lane within its half warp) of a tile diagonal (J = I + off) or
+    // antidiagonal (J = off - I); the two half warps walk two different tasks at the same time (phase_lines).
     // The tile `mid` (middle of an antidiagonal, which holds both members of its mirror pairs) enters with half weight
     // because the caller doubles the sums afterwards.  Measured and dropped (profiles/README.md, round 2): loading the
     // next tile's operands into the registers of the current one as its halves die, pinned with warp fences, and forcing
@@ -265,8 +266,8 @@ struct Ctx {
             r.k2 = *reinterpret_cast<const double2 *>(sk + o);
             return r;
         };
-        int I = lo + lane;
-        for (; I < hi; I += 32) {
+        int I = lo + (lane & 15);
+        for (; I < hi; I += 16) {
             const int J = DIAG ? I + off : off - I;
             Half x0 = ldh(I, 0), x1 = ldh(I, 1);
             const Half y0 = ldh(J, 0), y1 = ldh(J, 1);
@@ -300,14 +301,18 @@ struct Ctx {
         // partition carries the same work (tasks are dealt longest first in snake order)
         const int wpb = blockDim.x >> 5, hw = wpb >> 1, w = threadIdx.x >> 5, wstride = nchunk * wpb;
         const int wi = w < hw ? chunk * hw + w : wstride - 1 - (chunk * hw + w - hw);
+        // A warp takes a PAIR of neighbouring tasks of the same kind at a time, one per half warp (lam = 2 * pair + half): the
+        // cost outside the tile loop (first operand loads, zeroing, reduction, stores) is paid once per pair, and short
+        // tasks fill the lanes better.  The unit that is dealt is the pair: position t of the dealing order = 2 * pair + kind.
+        const int ncp = (nc + 1) >> 1, half = lane >> 4;
         for (int round = 0;; round++) {
             const int slot = round * wstride + ((round & 1) ? wstride - 1 - wi : wi);
             const int t = slot * world + (rank + slot) % world;   // position in the longest-first order; the rotation gives
                                                                   // every rank both kinds of task when world is even
-            if (round * wstride * world >= 2 * nc) break;
-            if (t >= 2 * nc) continue;
-            const int lam = t >> 1, kind = t & 1;            // task length nc - lam; kind 0: D = lam, 1: S = nc-lam-1
-            if (kind == 1 && nc - lam - 1 >= nanti) continue;
+            if (round * wstride * world >= 2 * ncp) break;
+            if (t >= 2 * ncp) continue;
+            const int lam = 2 * (t >> 1) + half, kind = t & 1;    // task length nc - lam; kind 0: D = lam, 1: S = nc-lam-1
+            const bool valid = lam < nc && !(kind == 1 && nc - lam - 1 >= nanti);
             double acc[3][8];
 #pragma unroll
             for (int m = 0; m < 3; m++)
@@ -318,51 +323,53 @@ struct Ctx {
                 // the mirror argument holds along an antidiagonal too: tiles I < J count twice; the middle tile (S even)
                 // holds both members of its pairs already and is walked with half weight
                 const int S = nc - lam - 1; task = nc + S;
-                tile_walk<false>(gsm, gs, 0, (S >> 1) + 1, S, (S & 1) ? -1 : (S >> 1), acc);
+                tile_walk<false>(gsm, gs, 0, valid ? (S >> 1) + 1 : 0, S, (S & 1) ? -1 : (S >> 1), acc);
 #pragma unroll
                 for (int m = 0; m < 3; m++)
 #pragma unroll
                     for (int i = 0; i < 7; i++) acc[m][i] += acc[m][i];
             }
-            else { task = lam; tile_walk<true>(gsm, gs, 0, nc - lam, lam, -1, acc); }
-            // 24 values (3 x 7 used) summed over the 32 lanes by halving: lanes exchange the half they do not keep
+            else { task = lam; tile_walk<true>(gsm, gs, 0, valid ? nc - lam : 0, lam, -1, acc); }
+            // 24 values (3 x 7 used) summed over the 16 lanes of a half warp by halving: lanes exchange the half they do not
+            // keep; both halves of the warp reduce their own task in the same shuffles
             double v12[12], v6[6], v4[4], v2[2];
             {
-                const bool up = lane & 16;
+                const bool up = lane & 8;
 #pragma unroll
                 for (int i = 0; i < 12; i++) {
                     const double lo = acc[i / 8][i % 8], hi = acc[(i + 12) / 8][(i + 12) % 8];
-                    const double got = __shfl_xor_sync(0xffffffffu, up ? lo : hi, 16);
+                    const double got = __shfl_xor_sync(0xffffffffu, up ? lo : hi, 8);
                     v12[i] = (up ? hi : lo) + got;
                 }
             }
             {
-                const bool up = lane & 8;
-#pragma unroll
-                for (int i = 0; i < 6; i++) { const double got = __shfl_xor_sync(0xffffffffu, up ? v12[i] : v12[i + 6], 8); v6[i] = (up ? v12[i + 6] : v12[i]) + got; }
-            }
-            {
                 const bool up = lane & 4;
 #pragma unroll
-                for (int i = 0; i < 3; i++) { const double got = __shfl_xor_sync(0xffffffffu, up ? v6[i] : v6[i + 3], 4); v4[i] = (up ? v6[i + 3] : v6[i]) + got; }
-                v4[3] = 0.0;
+                for (int i = 0; i < 6; i++) { const double got = __shfl_xor_sync(0xffffffffu, up ? v12[i] : v12[i + 6], 4); v6[i] = (up ? v12[i + 6] : v12[i]) + got; }
             }
             {
                 const bool up = lane & 2;
 #pragma unroll
-                for (int i = 0; i < 2; i++) { const double got = __shfl_xor_sync(0xffffffffu, up ? v4[i] : v4[i + 2], 2); v2[i] = (up ? v4[i + 2] : v4[i]) + got; }
+                for (int i = 0; i < 3; i++) { const double got = __shfl_xor_sync(0xffffffffu, up ? v6[i] : v6[i + 3], 2); v4[i] = (up ? v6[i + 3] : v6[i]) + got; }
+                v4[3] = 0.0;
             }
-            const bool up1 = lane & 1;
-            double tot = (up1 ? v2[1] : v2[0]) + __shfl_xor_sync(0xffffffffu, up1 ? v2[0] : v2[1], 1);
-            // this lane now holds value number vi of the flattened [3][8] accumulators
-            const int sub = (lane & 2 ? 2 : 0) + (lane & 1);
-            const int vi = (lane & 16 ? 12 : 0) + (lane & 8 ? 6 : 0) + (lane & 4 ? 3 : 0) + sub;
-            const int m = vi >> 3, idx = vi & 7;
-            if (sub < 3 && m < 3 && idx < 7) {
-                tot *= (m == 2) ? 2.0 * pab : pab;
-                const size_t w = ((size_t)task * 7 + idx) * 3 * NB + m * NB + e;
-                if (world == 1) P.Lsum[w] = tot;
-                else P.xpeer[rank][(size_t)(xepoch & 3u) * xwords + w] = tot;       // this rank's own buffer; the peers pull
+            {
+                const bool up = lane & 1;
+#pragma unroll
+                for (int i = 0; i < 2; i++) { const double got = __shfl_xor_sync(0xffffffffu, up ? v4[i] : v4[i + 2], 1); v2[i] = (up ? v4[i + 2] : v4[i]) + got; }
+            }
+            // this lane now holds the values number vi0, vi0 + 1 of the flattened [3][8] accumulators of its half's task
+            const int sub0 = (lane & 1) ? 2 : 0;
+            const int vi0 = (lane & 8 ? 12 : 0) + (lane & 4 ? 6 : 0) + (lane & 2 ? 3 : 0) + sub0;
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                const int vi = vi0 + i, m = vi >> 3, idx = vi & 7;
+                if (valid && sub0 + i < 3 && m < 3 && idx < 7) {
+                    const double tot = v2[i] * ((m == 2) ? 2.0 * pab : pab);
+                    const size_t w = ((size_t)task * 7 + idx) * 3 * NB + m * NB + e;
+                    if (world == 1) P.Lsum[w] = tot;
+                    else P.xpeer[rank][(size_t)(xepoch & 3u) * xwords + w] = tot;       // this rank's own buffer; the peers pull
+                }
             }
         }
         if (world > 1) {
@@ -435,7 +442,7 @@ struct Ctx {
             const int rec = 21 * NB;                               // words per task
             auto source = [&](size_t i) -> const double * {
                 const int task = (int)(i / rec);
-                const int t = task < nc ? 2 * task : 2 * (2 * nc - task - 1) + 1;       // position in the dealing order (phase_lines)
+                const int t = task < nc ? 2 * (task >> 1) : 2 * ((2 * nc - task - 1) >> 1) + 1;    // position of its pair in the dealing order (phase_lines)
                 const int slot = t / world, owner = ((t - slot * world) - slot % world + world) % world;
                 return P.xpeer[owner] + slot_off + i;
             };
