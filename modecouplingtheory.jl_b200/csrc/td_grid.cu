@@ -305,6 +305,7 @@ struct Ctx {
         // cost outside the tile loop (first operand loads, zeroing, reduction, stores) is paid once per pair, and short
         // tasks fill the lanes better.  The unit that is dealt is the pair: position t of the dealing order = 2 * pair + kind.
         const int ncp = (nc + 1) >> 1, half = lane >> 4;
+        const size_t l7 = (size_t)(nc + nanti) * 7;
         for (int round = 0;; round++) {
             const int slot = round * wstride + ((round & 1) ? wstride - 1 - wi : wi);
             const int t = slot * world + (rank + slot) % world;   // position in the longest-first order; the rotation gives
@@ -366,7 +367,7 @@ struct Ctx {
                 const int vi = vi0 + i, m = vi >> 3, idx = vi & 7;
                 if (valid && sub0 + i < 3 && m < 3 && idx < 7) {
                     const double tot = v2[i] * ((m == 2) ? 2.0 * pab : pab);
-                    const size_t w = ((size_t)task * 7 + idx) * 3 * NB + m * NB + e;
+                    const size_t w = (size_t)(m * NB + e) * l7 + (size_t)task * 7 + idx;          // [sequence][task][7]: see phase_scan
                     if (world == 1) P.Lsum[w] = tot;
                     else P.xpeer[rank][(size_t)(xepoch & 3u) * xwords + w] = tot;       // this rank's own buffer; the peers pull
                 }
@@ -391,7 +392,7 @@ struct Ctx {
         __shared__ double wtot[kGT / 32];
         const int Nk = P.Nk, world = P.world, nseq = 3 * NB;
         const int nc = grid_chunks(Nk);
-        const size_t xwords = grid_lsum_words(Nk, NS);
+        const size_t xwords = grid_lsum_words(Nk, NS), l7 = (size_t)(nc + grid_anti_tasks(Nk)) * 7;
         const double *lcur = P.Lsum;                           // sharded: filled by the landing pass below
         const long long t0 = clock64();
         // A line collects the entries of at most two tasks.  Increment of row ik (0-based): diagonal ik + diagonal -ik
@@ -402,12 +403,15 @@ struct Ctx {
             Row r;
             const int D0 = ik >> 2, rr = ik & 3;
             r.two_d = rr > 0 && D0 + 1 <= nc - 1;
-            r.w[0] = ((size_t)D0 * 7 + rr + 3) * nseq + c;
-            r.w[1] = ((size_t)(r.two_d ? D0 + 1 : D0) * 7 + (r.two_d ? rr - 1 : rr + 3)) * nseq + c;
+            const size_t cb = (size_t)c * l7;                    // the sums are stored [sequence][task][7]: consecutive rows of
+                                                                 // a sequence are neighbours in memory (14 instead of 32 sectors
+                                                                 // per warp load)
+            r.w[0] = cb + (size_t)D0 * 7 + rr + 3;
+            r.w[1] = cb + (size_t)(r.two_d ? D0 + 1 : D0) * 7 + (r.two_d ? rr - 1 : rr + 3);
             const int s_ = max(ik - 1, 0), S0 = s_ >> 2, q = s_ & 3;
             r.two_a = q <= 2 && S0 >= 1;
-            r.w[2] = ((size_t)(nc + S0) * 7 + q) * nseq + c;
-            r.w[3] = ((size_t)(nc + (r.two_a ? S0 - 1 : S0)) * 7 + (r.two_a ? q + 4 : q)) * nseq + c;
+            r.w[2] = cb + (size_t)(nc + S0) * 7 + q;
+            r.w[3] = cb + (size_t)(nc + (r.two_a ? S0 - 1 : S0)) * 7 + (r.two_a ? q + 4 : q);
             r.pos = ik > 0;
             if (!r.pos) { r.w[2] = r.w[0]; r.w[3] = r.w[0]; }          // row 0 has no antidiagonal: any valid word
             return r;
@@ -427,7 +431,7 @@ struct Ctx {
         if (world > 1) {
             // Landing pass of a k-sharded solve.  One thread per block waits for the arrival counter of this exchange (all
             // blocks of all ranks have announced); then the grid PULLS every task's sums from the buffer of the rank that
-            // computed it (NVLink loads from peer memory, unit stride within a task) into the local Lsum, and re-arms this
+            // computed it (NVLink loads from peer memory, 7 consecutive words per task and sequence) into the local Lsum, and re-arms this
             // rank's own buffer of two exchanges ahead.  Every word still validates itself (sentinel until stored).
             if (threadIdx.x == 0) {
                 const unsigned long long *cnt = (const unsigned long long *)(P.xpeer[P.rank] + 4 * xwords) + (xepoch & 3u);
@@ -439,9 +443,8 @@ struct Ctx {
             __syncthreads();
             const size_t slot_off = (size_t)(xepoch & 3u) * xwords;
             unsigned long long *clr = (unsigned long long *)(P.xpeer[P.rank] + (size_t)((xepoch + 2u) & 3u) * xwords);
-            const int rec = 21 * NB;                               // words per task
             auto source = [&](size_t i) -> const double * {
-                const int task = (int)(i / rec);
+                const int task = (int)((i % l7) / 7);              // [sequence][task][7]
                 const int t = task < nc ? 2 * (task >> 1) : 2 * ((2 * nc - task - 1) >> 1) + 1;    // position of its pair in the dealing order (phase_lines)
                 const int slot = t / world, owner = ((t - slot * world) - slot % world + world) % world;
                 return P.xpeer[owner] + slot_off + i;
