@@ -25,7 +25,7 @@ struct GridParams {
     double *C1, *C2, *C3, *Fold, *K0, *Fcur, *Kcur;   // [dof]
     double *G;                   // MC: F, G1, G2, G3 species-major [4][nb][Nk]
     double *Inc, *Tm;            // MC: increments and prefix sums [3*nb][Nk]
-    double *Lsum;                // task sums [tasks][7][3*nb]  (grid_lsum_words)
+    double *Lsum;                // task sums [3*nb sequences][tasks][7]  (grid_lsum_words)
     double *dFh;                 // bootstrap: dF history [2N+1][dof]
     unsigned long long *err;     // [2] rotating max-error words (bits of a non-negative double)
     double *F_out, *K_out;       // trajectory [nt][dof]  (mode 1/2: [dof])
