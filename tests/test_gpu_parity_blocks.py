@@ -119,6 +119,36 @@ def test_ddim_critical_point_2d_goldens_test_dDimMCT_crit_pt_96_97():
     assert out[0.69] < 1e-7                                                              # :97
 
 
+def test_ddim_critical_point_5d_goldens_test_dDimMCT_crit_pt_133_134():
+    """d = 5 with Leutheusser's Percus-Yevick c(k) (test/test_dDimMCT_crit_pt.jl:25-47, :100-134) through the device's
+    steady-state solver."""
+    k = P.sf.wavenumber_grid(100)
+
+    def ck5d(eta):
+        T = 1 + 18 * eta + 6 * eta ** 2
+        Q0 = 1 / (120 * eta * (1 - eta) ** 3) * (1 - 33 * eta - 87 * eta ** 2 - 6 * eta ** 3 - T ** 1.5)
+        Q1 = -1 / (12 * (1 - eta) ** 3) * ((3 + 2 * eta) * T ** 0.5 + 3 + 19 * eta + 3 * eta ** 2)
+        Q2 = -T ** 0.5 / (24 * (1 - eta) ** 3) * (2 + 3 * eta + T ** 0.5)
+        c0 = -(-8 * Q2) ** 2
+        c1 = 120 * eta * Q0 ** 2
+        c3 = 20 * eta * (8 * Q0 * Q2 - 3 * Q1 ** 2)
+        c5 = -3 / 8 * eta * c0
+        return -(1 / k ** 10) * 8 * np.pi ** 2 * (
+            8 * (720 * c5 - 18 * c3 * k ** 2 + c1 * k ** 4)
+            + (-5760 * c5 + 144 * (c3 + 20 * c5) * k ** 2 - 8 * (c1 + 9 * c3 + 30 * c5) * k ** 4 + (3 * c0 + 4 * c1 + 6 * c3 + 8 * c5) * k ** 6) * np.cos(k)
+            + k * (-5760 * c5 + 48 * (3 * c3 + 20 * c5) * k ** 2 - (3 * c0 + 8 * (c1 + 3 * c3 + 6 * c5)) * k ** 4 + (c0 + c1 + c3 + c5) * k ** 6) * np.sin(k))
+
+    out = {}
+    for phi in (0.25, 0.26):
+        rho = 60 * phi / np.pi ** 2
+        ck = ck5d(phi)
+        Sk = 1 + rho * ck / (1 - rho * ck)
+        kern = pkg.dDimModeCouplingKernel(rho, 1.0, 1.0, k, Sk, 5)
+        out[phi] = pkg.solve_steady_state(k ** 2 / Sk, Sk, kern, tolerance=1e-8).F.sum()
+    assert out[0.26] == pytest.approx(33.463940782589255, rel=RTOL)                      # test/test_dDimMCT_crit_pt.jl:133
+    assert out[0.25] < 1e-7                                                              # :134
+
+
 def test_ddim_time_doubling_vs_oracle():
     p = P.hard_spheres(24, 0.50)
     e = P.overdamped(p)
