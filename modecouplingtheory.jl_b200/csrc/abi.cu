@@ -138,6 +138,7 @@ struct mct_equation_s {
     // block-valued / dense kernels (td_grid.cu): one allocation holding coefficients and workspace
     int ns = 1;
     double *d_gws = nullptr;
+    int *d_deal = nullptr; size_t deal_cap = 0; int deal_nsm = 0;      // inside d_gws: the host's deal of the line-sum tasks (grid_upload_deal)
     GridParams gp{};
     // k-sharding over GPUs: this rank's exchange buffer (IPC-exported) and the peers' mappings
     double *d_xshard = nullptr;
@@ -610,6 +611,20 @@ static int expand_coef_blocks(int kind, double lam, const double *arr, int Nk, i
     return MCT_OK;
 }
 
+// The host's deal of the line-sum tasks for this equation's (rank, world) on a grid of one block per SM (td_grid.cu,
+// grid_build_deal); a table that does not fit the reserved space leaves the kernel on its closed-form deal.
+static int grid_upload_deal(mct_equation_t q) {
+    GridParams &g = q->gp;
+    g.deal = nullptr; g.deal_grid = 0;
+    if (g.type != GK_MC3D || !q->d_deal || env_int("MCT_GRID_DEAL", 1) == 0) return MCT_OK;
+    std::vector<int> table; int wsmax = 0, stride = 0;
+    grid_build_deal(g.Nk, g.ns, g.rank, g.world, q->deal_nsm, table, wsmax, stride);
+    if (table.size() > q->deal_cap) return MCT_OK;
+    MCT_CUDA(cudaMemcpy(q->d_deal, table.data(), table.size() * sizeof(int), cudaMemcpyHostToDevice));
+    g.deal = q->d_deal; g.deal_grid = q->deal_nsm; g.deal_wsmax = wsmax; g.deal_stride = stride;
+    return MCT_OK;
+}
+
 // Fills q->gp and allocates its workspace.  mode 0: time doubling (needs opts), 1: steady state, 2: one evaluation.
 static int grid_setup(mct_equation_t q, mct_kernel_t h, int mode, const std::vector<double> &coef_host /* [6][dof] */) {
     const int Nk = h->Nk, ns = h->Ns, nb = ns * ns;
@@ -619,7 +634,8 @@ static int grid_setup(mct_equation_t q, mct_kernel_t h, int mode, const std::vec
     const size_t traj = (mode == 0) ? (size_t)q->nt * dof : dof;
     const size_t lsum = grid_lsum_words(Nk, ns);
     const size_t dfh = (mode == 0) ? (size_t)(2 * N + 1) * dof : 0;
-    const size_t total = 6 * dof + 4 * ring + 7 * dof + 4 * dof + 6 * dof + lsum + dfh + 2 * traj + 40;
+    const size_t deal_cap = (h->type == K_MC3D) ? grid_deal_capacity(Nk, ns, h->n_sm) : 0;      // ints, behind everything else
+    const size_t total = 6 * dof + 4 * ring + 7 * dof + 4 * dof + 6 * dof + lsum + dfh + 2 * traj + 40 + (deal_cap + 1) / 2;
     MCT_CUDA(cudaMalloc(&q->d_gws, total * sizeof(double)));
     cudaError_t e_init = cudaMemset(q->d_gws, 0, total * sizeof(double));
     if (e_init == cudaSuccess) e_init = cudaMemcpy(q->d_gws, coef_host.data(), 6 * dof * sizeof(double), cudaMemcpyHostToDevice);
@@ -642,7 +658,8 @@ static int grid_setup(mct_equation_t q, mct_kernel_t h, int mode, const std::vec
     g.err = (unsigned long long *)p; p += 2;
     g.status = (int *)p; g.kernel_evals = (long long *)(p + 2); g.prof = (unsigned long long *)(p + 4); g.xepoch_state = (unsigned *)(p + 32);
     q->d_F = g.F_out; q->d_K = g.K_out;
-    return MCT_OK;
+    q->d_deal = (int *)(p + 38); q->deal_cap = deal_cap; q->deal_nsm = h->n_sm;      // p + 38 = end of the 40 doubles that start at g.err
+    return grid_upload_deal(q);
 }
 
 static int grid_run(mct_equation_t q, long long *evals, int *status, float *device_ms) {
@@ -1278,7 +1295,7 @@ int mct_equation_shard_prepare(mct_equation_t q, int rank, int world, unsigned c
     static_assert(sizeof(hd) == 64, "cudaIpcMemHandle_t is 64 bytes");
     memcpy(handle_out, &hd, 64);
     q->gp.rank = rank; q->gp.world = world;
-    return MCT_OK;
+    return grid_upload_deal(q);
 }
 
 int mct_equation_shard_connect(mct_equation_t q, const unsigned char *handles) {

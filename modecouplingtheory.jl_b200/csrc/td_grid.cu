@@ -17,6 +17,9 @@
 // config-4 evaluation: the wait is the arrival skew of the blocks, not the barrier), so cg's is kept.
 #include <cooperative_groups.h>
 
+#include <algorithm>
+#include <utility>
+
 #include "td_grid.cuh"
 
 namespace cg = cooperative_groups;
@@ -25,7 +28,7 @@ namespace mct {
 
 namespace {
 
-constexpr int kGT = 256;        // threads per block
+constexpr int kGT = kGridThreads;   // threads per block
 
 // C = A*B, column-major NS x NS, plain left-to-right sums (StaticArrays `*`); everything stays in registers
 template <int NS>
@@ -306,11 +309,17 @@ struct Ctx {
         // tasks fill the lanes better.  The unit that is dealt is the pair: position t of the dealing order = 2 * pair + kind.
         const int ncp = (nc + 1) >> 1, half = lane >> 4;
         const size_t l7 = (size_t)(nc + nanti) * 7;
+        const int *mine = (P.deal != nullptr && (int)gridDim.x == P.deal_grid && blockDim.x == kGridThreads)
+                              ? P.deal + ((size_t)e * P.deal_wsmax + chunk * wpb + w) * P.deal_stride : nullptr;
         for (int round = 0;; round++) {
-            const int slot = round * wstride + ((round & 1) ? wstride - 1 - wi : wi);
+            int slot;
+            if (mine) { slot = __ldg(mine + round); if (slot < 0) break; }                 // the host's deal (grid_build_deal)
+            else {
+                slot = round * wstride + ((round & 1) ? wstride - 1 - wi : wi);
+                if (round * wstride * world >= 2 * ncp) break;
+            }
             const int t = slot * world + (rank + slot) % world;   // position in the longest-first order; the rotation gives
                                                                   // every rank both kinds of task when world is even
-            if (round * wstride * world >= 2 * ncp) break;
             if (t >= 2 * ncp) continue;
             const int lam = 2 * (t >> 1) + half, kind = t & 1;    // task length nc - lam; kind 0: D = lam, 1: S = nc-lam-1
             const bool valid = lam < nc && !(kind == 1 && nc - lam - 1 >= nanti);
@@ -846,6 +855,64 @@ int ddim_fuse_table(int Nk, double prefactor, const double *dV, const double *dJ
     count_launch();
     MCT_CUDA(cudaGetLastError());
     return MCT_OK;
+}
+
+// tile rounds of the pair at position t of the dealing order (the longer of its two half-warp tasks); mirrors phase_lines
+static int deal_rounds(int t, int nc, int nanti) {
+    const int pair = t >> 1, kind = t & 1;
+    int r = 0;
+    for (int h = 0; h < 2; h++) {
+        const int lam = 2 * pair + h;
+        if (lam >= nc) continue;
+        int L;
+        if (kind) { const int S = nc - lam - 1; if (S >= nanti) continue; L = (S >> 1) + 1; }
+        else L = nc - lam;
+        r = std::max(r, (L + 15) / 16);
+    }
+    return r;
+}
+
+void grid_build_deal(int Nk, int ns, int rank, int world, int grid, std::vector<int> &table, int &wsmax, int &stride) {
+    const int nb = ns * ns, wpb = kGridThreads / 32, hw = wpb / 2;
+    const int nc = grid_chunks(Nk), nanti = grid_anti_tasks(Nk), ncp = (nc + 1) / 2;
+    wsmax = ((grid + nb - 1) / nb) * wpb;
+    const double ovh = 1.5;      // rounds; the measured time does not depend on it between 0 and 5
+    // this rank's slots with their cost: tile rounds + `ovh` rounds for what a pair costs outside the tile loop
+    std::vector<std::pair<double, int>> slots;
+    for (int s = 0; (long long)s * world < 2 * ncp; s++) {
+        const int t = s * world + (rank + s) % world;
+        if (t >= 2 * ncp) continue;
+        const int r = deal_rounds(t, nc, nanti);
+        if (r > 0) slots.push_back({r + ovh, s});
+    }
+    std::stable_sort(slots.begin(), slots.end(), [](const std::pair<double, int> &a, const std::pair<double, int> &b) { return a.first > b.first; });
+    std::vector<std::vector<std::vector<int>>> lists(nb);      // [e][warp] -> slots
+    size_t longest = 0;
+    for (int e = 0; e < nb; e++) {
+        const int nchunk = grid > e ? (grid - e + nb - 1) / nb : 0, ws = nchunk * wpb;
+        lists[e].assign(ws, {});
+        if (ws == 0) continue;
+        std::vector<double> bin(nchunk * hw, 0.0), wl(ws, 0.0);
+        for (const auto &cs : slots) {
+            const int b = (int)(std::min_element(bin.begin(), bin.end()) - bin.begin());
+            const int chunk = b / hw, w0 = chunk * wpb + b % hw, w1 = w0 + hw;     // the two warps of that SM partition
+            const int wsel = wl[w0] <= wl[w1] ? w0 : w1;
+            bin[b] += cs.first; wl[wsel] += cs.first;
+            lists[e][wsel].push_back(cs.second);
+        }
+        for (const auto &l : lists[e]) longest = std::max(longest, l.size());
+    }
+    stride = (int)longest + 1;
+    table.assign((size_t)nb * wsmax * stride, -1);
+    for (int e = 0; e < nb; e++)
+        for (size_t w = 0; w < lists[e].size(); w++)
+            std::copy(lists[e][w].begin(), lists[e][w].end(), table.begin() + ((size_t)e * wsmax + w) * stride);
+}
+
+size_t grid_deal_capacity(int Nk, int ns, int grid) {      // the single-GPU table is the largest; a few entries of slack per warp
+    std::vector<int> t; int wsmax = 0, stride = 0;
+    grid_build_deal(Nk, ns, 0, 1, grid, t, wsmax, stride);
+    return t.size() + (size_t)ns * ns * wsmax * 4;
 }
 
 int td_grid_launch(const GridParams &P, int n_sm, cudaStream_t stream) {

@@ -1,6 +1,8 @@
 // td_grid.cuh -- whole-grid cooperative solver for the kernels whose degrees of freedom are Ns x Ns blocks per
 // wavenumber (MultiComponentModeCouplingKernel3D) or whose evaluation is a dense triple sum (dDimModeCouplingKernel).
 #pragma once
+#include <vector>
+
 #include "common.cuh"
 
 namespace mct {
@@ -44,7 +46,12 @@ struct GridParams {
     unsigned *xepoch_state;      // exchange epoch carried from one solve of a sharded equation to the next (the rotating
                                  // buffers of all ranks stay in step without a host-side re-arm)
     unsigned long long *prof;    // [12] cycles per phase seen by thread 0 (diagnostics, printed with MCT_GRID_PROF=1)
+    // line-sum tasks dealt by the host (grid_build_deal): list of dealing-order slots of warp wl of species pair e at
+    // deal[(e * deal_wsmax + wl) * deal_stride + j], terminated by -1; valid for a grid of deal_grid blocks of kGridThreads
+    // threads (any other launch shape, or deal == nullptr, falls back to the closed-form snake deal)
+    const int *deal; int deal_grid, deal_wsmax, deal_stride;
 };
+constexpr int kGridThreads = 256;
 
 // Multi-component line sums are produced per tile task (td_grid.cu, phase_lines): 4-wavenumber chunks, one task per tile
 // diagonal J - I >= 0 (tasks [0, chunks)) and per tile antidiagonal that holds a line s <= Nk-2 (tasks chunks + S),
@@ -55,6 +62,11 @@ __host__ __device__ inline int grid_anti_tasks(int Nk) { return Nk >= 2 ? (Nk - 
 __host__ __device__ inline size_t grid_lsum_words(int Nk, int ns) {
     return (size_t)(grid_chunks(Nk) + grid_anti_tasks(Nk)) * 7 * 3 * ns * ns;
 }
+
+// Host side of the deal: longest-processing-time-first assignment of this rank's task pairs to the SM partitions of every
+// species pair's blocks, then to the lighter of the partition's two warps.  Returns the table (see GridParams::deal).
+void grid_build_deal(int Nk, int ns, int rank, int world, int grid, std::vector<int> &table, int &wsmax, int &stride);
+size_t grid_deal_capacity(int Nk, int ns, int grid);     // ints to reserve (any rank / world)
 
 int td_grid_launch(const GridParams &P, int n_sm, cudaStream_t stream);
 
